@@ -1,0 +1,103 @@
+/*
+ * saver_cuda.h -- C ABI of libsaver_cuda, the B200 (sm_100a) implementation of SAVER's
+ * per-gene expression-recovery hot path.
+ *
+ * The reference (mohuangx/SAVER, /root/reference) is pure R and has no FFI of its own; the
+ * boundary it exposes for this path is its R function API (NAMESPACE:3-23).  Each entry
+ * point below is what a `.Call` shim binds to replace the body of one of those functions
+ * (INTEGRATION.md shows the shim).  Conventions:
+ *   - plain C types only; no R, torch or CUDA types cross the boundary;
+ *   - matrices are column-major fp64 like R's: a "panel" of B genes over n cells is n x B
+ *     (one gene = one contiguous column); the design is n x p;
+ *   - all buffers are caller-owned; the library keeps no host pointer past return;
+ *   - every function returns 0 on success or a negative SAVER_ERR_* code;
+ *     saver_cuda_last_error() gives the message.  Per-gene solver trouble is NOT an error:
+ *     it is reported in per-gene status arrays, and the host mirrors the reference's
+ *     tryCatch fallbacks (R/expr_predict.R:44-52, R/calc_posterior.R:41-49);
+ *   - `device_ptrs` != 0 means every array argument of that call already lives on the
+ *     handle's device (used by bench.py's HBM-resident timing and by the NCCL plumbing);
+ *     an R host always passes 0;
+ *   - there is no CPU fallback: without a usable CUDA device saver_cuda_create fails.
+ */
+#ifndef SAVER_CUDA_H
+#define SAVER_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SAVER_API __attribute__((visibility("default")))
+#else
+#define SAVER_API
+#endif
+
+#define SAVER_ABI_VERSION 1
+
+#define SAVER_OK 0
+#define SAVER_ERR_CUDA (-1)     /* CUDA runtime failure (message has the CUDA error) */
+#define SAVER_ERR_ARG (-2)      /* invalid argument */
+#define SAVER_ERR_STATE (-3)    /* call order (e.g. design not set) */
+#define SAVER_ERR_NOMEM (-4)    /* device or host allocation failed */
+
+/* model codes of calc.loglik.* / calc.a|b|k */
+#define SAVER_MODEL_A 0
+#define SAVER_MODEL_B 1
+#define SAVER_MODEL_K 2
+
+/* per-gene info record written by saver_cuda_calc_post (doubles) */
+#define SAVER_POST_INFO 8
+/*  [0] chosen model: 0 a, 1 b, 2 k, 3 constant-mu branch (calc.b only), -1 all-zero gene
+ *  [1] prior parameter of the chosen model (1/a, 1/b or k)
+ *  [2..4] negative log-likelihood of a, b, k (NaN if not fitted)
+ *  [5] bitmask: model m took the grid ("stochastic fallback") branch
+ *  [6] number of log-likelihood evaluations
+ *  [7] bitmask: model m raised an R error (dropped, as tryCatch -> c(0, Inf))            */
+
+typedef struct saver_cuda_ctx* saver_cuda_handle;
+
+/* ---- lifecycle ---- */
+SAVER_API int saver_cuda_abi_version(void);
+/* One handle per CUDA device (one process per GPU). */
+SAVER_API int saver_cuda_create(int device, saver_cuda_handle* out);
+SAVER_API int saver_cuda_destroy(saver_cuda_handle h);
+SAVER_API const char* saver_cuda_last_error(saver_cuda_handle h);
+/* Block until all work queued by this handle has finished. */
+SAVER_API int saver_cuda_synchronize(saver_cuda_handle h);
+/* The cudaStream_t the handle launches on (as void*), for callers that time with events. */
+SAVER_API int saver_cuda_stream(saver_cuda_handle h, void** stream);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+SAVER_API long long saver_cuda_launch_count(saver_cuda_handle h);
+
+/* ---- calc.loglik.a/b/k (R/calc_loglik.R:26,44,61): out = -loglik(param) ----
+ * mu_len / sf_len are 1 (recycled scalar, R/calc_loglik.R:28-33) or n.  Host pointers. */
+SAVER_API int saver_cuda_loglik(saver_cuda_handle h, int model, double param, const double* y,
+                      const double* mu, int mu_len, const double* sf, int sf_len, int n,
+                      double* out);
+
+/* ---- calc.a / calc.b / calc.k (R/optimize_variance.R:24,61,101) ----
+ * out2 = c(1/a | 1/b | k, nll).  flags: bit0 grid branch, bit1 uniroot used, bit2 the R
+ * code would have raised (out2 = (0, Inf)).  grid200 (optional): the 100 grid points then
+ * their 100 log-likelihoods, so an R host can draw sample() itself (optimize_variance.R:53);
+ * the library uses the expectation sum(samp * p).  Host pointers. */
+SAVER_API int saver_cuda_calc_var(saver_cuda_handle h, int model, const double* y, const double* mu,
+                        int mu_len, const double* sf, int sf_len, int n, double* out2,
+                        int* flags, double* grid200);
+
+/* ---- calc.post (R/calc_posterior.R:26) for a panel of B genes ----
+ * Y: n x B raw counts.  MU: n x B predictions, or B scalars when mu_is_scalar != 0
+ * (R/calc_posterior.R:28-30).  sf: n size factors.  est (required), se (NULL when
+ * estimates.only): n x B, ceiling(v * 1000 * scale_sf) / 1000.  est_raw / se_raw (optional):
+ * the same before the ceiling.  info (optional): SAVER_POST_INFO x B.  grid (optional):
+ * 600 x B, per model 100 grid points + 100 log-liks (only filled for grid-branch models). */
+SAVER_API int saver_cuda_calc_post(saver_cuda_handle h, const double* Y, const double* MU,
+                         int mu_is_scalar, const double* sf, int n, int B, double scale_sf,
+                         double* est, double* se, double* est_raw, double* se_raw,
+                         double* info, double* grid, int device_ptrs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAVER_CUDA_H */

@@ -1,0 +1,279 @@
+// saver_cuda.cu -- the C ABI of libsaver_cuda (include/saver_cuda.h).
+// Marshals caller buffers to the device, launches the kernels, copies results back.
+#include "../../include/saver_cuda.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "saver_kernels.h"
+
+using namespace saver;
+
+struct saver_cuda_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  char err[512] = {0};
+  DesignState design;
+};
+
+namespace {
+
+int fail(saver_cuda_ctx* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof h->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? SAVER_ERR_NOMEM : SAVER_ERR_CUDA, \
+                  "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+  } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync pool keeps freed blocks cached).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaStream_t s = nullptr;
+  cudaError_t alloc(size_t count, cudaStream_t stream) {
+    s = stream;
+    if (count == 0) count = 1;
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+// Input array that is either already on the device or must be uploaded.
+template <typename T>
+struct InArr {
+  DevBuf<T> buf;
+  const T* d = nullptr;
+  cudaError_t bind(const T* src, size_t count, bool on_device, cudaStream_t s) {
+    if (!src) { d = nullptr; return cudaSuccess; }
+    if (on_device) { d = src; return cudaSuccess; }
+    cudaError_t e = buf.alloc(count, s);
+    if (e != cudaSuccess) return e;
+    d = buf.p;
+    return cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+// Output array: device-resident caller buffer, or a temp that is copied back.
+template <typename T>
+struct OutArr {
+  DevBuf<T> buf;
+  T* d = nullptr;
+  T* host = nullptr;
+  size_t count = 0;
+  cudaError_t bind(T* dst, size_t n, bool on_device, cudaStream_t s) {
+    count = n;
+    if (!dst) { d = nullptr; return cudaSuccess; }
+    if (on_device) { d = dst; return cudaSuccess; }
+    host = dst;
+    cudaError_t e = buf.alloc(n, s);
+    d = buf.p;
+    return e;
+  }
+  cudaError_t fetch(cudaStream_t s) {
+    if (!host || !d) return cudaSuccess;
+    return cudaMemcpyAsync(host, d, count * sizeof(T), cudaMemcpyDeviceToHost, s);
+  }
+};
+
+__global__ void fill_panel_kernel(double* dst, const double* scalars, int n, int B) {
+  const size_t tot = (size_t)n * B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot;
+       i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = scalars[i / n];
+}
+
+}  // namespace
+
+extern "C" {
+
+int saver_cuda_abi_version(void) { return SAVER_ABI_VERSION; }
+
+int saver_cuda_create(int device, saver_cuda_handle* out) {
+  if (!out) return SAVER_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return SAVER_ERR_CUDA;
+  saver_cuda_ctx* h = new (std::nothrow) saver_cuda_ctx();
+  if (!h) return SAVER_ERR_NOMEM;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return SAVER_ERR_CUDA;
+  }
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  *out = h;
+  return SAVER_OK;
+}
+
+int saver_cuda_destroy(saver_cuda_handle h) {
+  if (!h) return SAVER_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->design.release();
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return SAVER_OK;
+}
+
+const char* saver_cuda_last_error(saver_cuda_handle h) { return h ? h->err : "null handle"; }
+
+int saver_cuda_synchronize(saver_cuda_handle h) {
+  if (!h) return SAVER_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return SAVER_OK;
+}
+
+int saver_cuda_stream(saver_cuda_handle h, void** stream) {
+  if (!h || !stream) return SAVER_ERR_ARG;
+  *stream = (void*)h->stream;
+  return SAVER_OK;
+}
+
+long long saver_cuda_launch_count(saver_cuda_handle h) { return h ? h->launches : 0; }
+
+static int one_gene(saver_cuda_handle h, int mode, int model, double param, const double* y,
+                    const double* mu, int mu_len, const double* sf, int sf_len, int n,
+                    double* out4, double* grid200) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!y || !mu || !sf || n < 2 || model < 0 || model > 2 || (mu_len != 1 && mu_len != n) ||
+      (sf_len != 1 && sf_len != n))
+    return fail(h, SAVER_ERR_ARG, "loglik/calc_var: bad arguments");
+  CU(cudaSetDevice(h->device));
+  std::vector<double> hm(n), hs(n);
+  for (int i = 0; i < n; ++i) {
+    hm[i] = mu_len == 1 ? mu[0] : mu[i];
+    hs[i] = sf_len == 1 ? sf[0] : sf[i];
+  }
+  InArr<double> dy, dm, ds;
+  CU(dy.bind(y, n, false, h->stream));
+  CU(dm.bind(hm.data(), n, false, h->stream));
+  CU(ds.bind(hs.data(), n, false, h->stream));
+  DevBuf<double> dout, dgrid;
+  DevBuf<int> nz;
+  CU(dout.alloc(4, h->stream));
+  CU(dgrid.alloc(200, h->stream));
+  CU(nz.alloc(n, h->stream));
+  CU(cudaMemsetAsync(dgrid.p, 0xff, 200 * sizeof(double), h->stream));  // NaN fill
+  LogLikArgs A{dy.d, dm.d, ds.d, n, model, mode, param, dout.p, dgrid.p, nz.p};
+  CU(launch_loglik(A, h->stream));
+  h->launches += 1;
+  CU(cudaMemcpyAsync(out4, dout.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (grid200)
+    CU(cudaMemcpyAsync(grid200, dgrid.p, 200 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SAVER_OK;
+}
+
+int saver_cuda_loglik(saver_cuda_handle h, int model, double param, const double* y,
+                      const double* mu, int mu_len, const double* sf, int sf_len, int n,
+                      double* out) {
+  if (!out) return fail(h, SAVER_ERR_ARG, "loglik: out is NULL");
+  double o4[4];
+  int rc = one_gene(h, 0, model, param, y, mu, mu_len, sf, sf_len, n, o4, nullptr);
+  if (rc == SAVER_OK) *out = o4[0];
+  return rc;
+}
+
+int saver_cuda_calc_var(saver_cuda_handle h, int model, const double* y, const double* mu,
+                        int mu_len, const double* sf, int sf_len, int n, double* out2,
+                        int* flags, double* grid200) {
+  if (!out2) return fail(h, SAVER_ERR_ARG, "calc_var: out2 is NULL");
+  double o4[4];
+  int rc = one_gene(h, 1, model, 0.0, y, mu, mu_len, sf, sf_len, n, o4, grid200);
+  if (rc == SAVER_OK) {
+    out2[0] = o4[0];
+    out2[1] = o4[1];
+    if (flags) *flags = (int)o4[2];
+  }
+  return rc;
+}
+
+int saver_cuda_calc_post(saver_cuda_handle h, const double* Y, const double* MU,
+                         int mu_is_scalar, const double* sf, int n, int B, double scale_sf,
+                         double* est, double* se, double* est_raw, double* se_raw,
+                         double* info, double* grid, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!Y || !MU || !sf || !est || n < 2 || B < 0)
+    return fail(h, SAVER_ERR_ARG, "calc_post: bad arguments");
+  if (B == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)n * B;
+  InArr<double> dY, dMU, dsf;
+  CU(dY.bind(Y, nb, dev, s));
+  CU(dsf.bind(sf, n, dev, s));
+  DevBuf<double> mu_panel;
+  const double* mu_d;
+  if (mu_is_scalar) {
+    CU(dMU.bind(MU, B, dev, s));
+    CU(mu_panel.alloc(nb, s));
+    fill_panel_kernel<<<592, 256, 0, s>>>(mu_panel.p, dMU.d, n, B);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    mu_d = mu_panel.p;
+  } else {
+    CU(dMU.bind(MU, nb, dev, s));
+    mu_d = dMU.d;
+  }
+  OutArr<double> oE, oS, oER, oSR, oI, oG;
+  CU(oE.bind(est, nb, dev, s));
+  CU(oS.bind(se, nb, dev, s));
+  CU(oER.bind(est_raw, nb, dev, s));
+  CU(oSR.bind(se_raw, nb, dev, s));
+  DevBuf<double> info_tmp;
+  double* info_d;
+  if (info) {
+    CU(oI.bind(info, (size_t)kPostInfo * B, dev, s));
+    info_d = oI.d;
+  } else {
+    CU(info_tmp.alloc((size_t)kPostInfo * B, s));
+    info_d = info_tmp.p;
+  }
+  CU(oG.bind(grid, (size_t)600 * B, dev, s));
+  if (oG.d) CU(cudaMemsetAsync(oG.d, 0xff, (size_t)600 * B * sizeof(double), s));
+  int stage;
+  calc_post_smem_bytes(n, &stage);
+  DevBuf<int> nz;
+  if (stage == 0) CU(nz.alloc(nb, s));
+  CalcPostArgs A{dY.d, mu_d, dsf.d, n, B, scale_sf, oE.d, oS.d, oER.d, oSR.d, info_d, oG.d, nz.p};
+  CU(launch_calc_post(A, s));
+  h->launches += 1;
+  CU(oE.fetch(s));
+  CU(oS.fetch(s));
+  CU(oER.fetch(s));
+  CU(oSR.fetch(s));
+  CU(oI.fetch(s));
+  CU(oG.fetch(s));
+  if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}
+
+}  // extern "C"

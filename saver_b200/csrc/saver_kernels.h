@@ -1,0 +1,51 @@
+// Internal launch interfaces between the C-ABI layer (saver_cuda.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace saver {
+
+constexpr int kPostInfo = 8;  // per-gene info record of calc_post (doubles)
+
+struct CalcPostArgs {
+  const double* Y;    // n x B raw counts (device)
+  const double* MU;   // n x B predictions (device)
+  const double* sf;   // n size factors (device)
+  int n, B;
+  double scale_sf;
+  double* EST;        // n x B (ceiling-quantised), required
+  double* SE;         // n x B or null (estimates.only)
+  double* EST_RAW;    // optional pre-ceiling outputs (parity tests)
+  double* SE_RAW;
+  double* INFO;       // kPostInfo x B: method, param, nll a/b/k, fallback mask, #evals, error mask
+  double* GRID;       // optional 600 x B: per model 100 grid points + 100 log-liks
+  int* nz_ws;         // n x B ints, only used when n is too large to stage (STAGE 0)
+};
+
+struct LogLikArgs {
+  const double *y, *mu, *sf;  // device, length n
+  int n, model, mode;         // mode 0: loglik(param); mode 1: calc.a/b/k
+  double param;
+  double* out;                // 4 doubles (device)
+  double* grid;               // optional 200 doubles (device)
+  int* nz_ws;                 // n ints (device)
+};
+
+// The shared design: x.est of R/saver.R:156-157, standardised once over all cells.
+struct DesignState {
+  int n = 0, p = 0;
+  double* Xs = nullptr;     // n x p column-major, (x - mean) / sd_n  (sd with 1/n); constant columns -> 0
+  double* xmean = nullptr;  // p
+  double* xsd = nullptr;    // p (0 marks a constant column)
+  void release() {
+    cudaFree(Xs); cudaFree(xmean); cudaFree(xsd);
+    Xs = xmean = xsd = nullptr;
+    n = p = 0;
+  }
+};
+
+size_t calc_post_smem_bytes(int n, int* stage);
+cudaError_t launch_calc_post(const CalcPostArgs& A, cudaStream_t stream);
+cudaError_t launch_loglik(const LogLikArgs& A, cudaStream_t stream);
+
+}  // namespace saver

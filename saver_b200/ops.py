@@ -1,0 +1,91 @@
+"""Thin Python calls over the C ABI (one function per export of include/saver_cuda.h).
+
+Panels are passed gene-major: a C-contiguous numpy array of shape (B, n) is exactly the
+n x B column-major panel of the C side.  torch CUDA tensors of the same shape are accepted
+wherever the ABI has ``device_ptrs`` (everything stays on the device then).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import default_handle, is_device, ptr
+
+POST_INFO = 8
+_D = C.c_double
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _vec(v, n):
+    v = np.atleast_1d(np.asarray(v, dtype=np.float64))
+    if v.size not in (1, n):
+        raise ValueError("length must be 1 or %d" % n)
+    return np.ascontiguousarray(v)
+
+
+def loglik(model, param, y, mu, sf, handle=None):
+    """calc.loglik.a/b/k (R/calc_loglik.R:26,44,61).  Scalars mu/sf are recycled."""
+    h = handle or default_handle()
+    y = _f64(y)
+    n = y.size
+    mu, sf = _vec(mu, n), _vec(sf, n)
+    out = _D(0.0)
+    h.check(h.lib.saver_cuda_loglik(h.h, int(model), _D(float(param)), ptr(y), ptr(mu), mu.size,
+                                    ptr(sf), sf.size, n, C.byref(out)))
+    return out.value
+
+
+def calc_var(model, y, mu, sf, want_grid=False, handle=None):
+    """calc.a / calc.b / calc.k (R/optimize_variance.R) -> (param, nll, flags[, grid])."""
+    h = handle or default_handle()
+    y = _f64(y)
+    n = y.size
+    mu, sf = _vec(mu, n), _vec(sf, n)
+    out = np.zeros(2)
+    flags = C.c_int(0)
+    grid = np.zeros(200) if want_grid else None
+    h.check(h.lib.saver_cuda_calc_var(h.h, int(model), ptr(y), ptr(mu), mu.size, ptr(sf), sf.size,
+                                      n, ptr(out), C.byref(flags), ptr(grid)))
+    if want_grid:
+        return out[0], out[1], flags.value, grid
+    return out[0], out[1], flags.value
+
+
+def calc_post(Y, MU, sf, scale_sf=1.0, want_se=True, want_raw=False, want_info=True,
+              want_grid=False, out=None, handle=None):
+    """calc.post (R/calc_posterior.R:26) for a panel: Y (B, n) raw counts, MU (B, n) or (B,).
+
+    Returns dict(est, se, est_raw, se_raw, info, grid); absent pieces are None.  With torch
+    CUDA tensors as inputs the outputs are torch CUDA tensors and nothing is copied.
+    """
+    h = handle or default_handle()
+    dev = is_device(Y)
+    if dev:
+        import torch
+        B, n = Y.shape
+        scalar = MU.dim() == 1
+        mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=Y.device)  # noqa: E731
+        assert Y.is_contiguous() and MU.is_contiguous() and sf.is_contiguous()
+        assert Y.dtype == torch.float64 and MU.dtype == torch.float64 and sf.dtype == torch.float64
+    else:
+        Y = _f64(np.atleast_2d(Y))
+        B, n = Y.shape
+        MU = _f64(MU)
+        scalar = MU.ndim == 1 and not (B == 1 and MU.size == n and n != 1)
+        if not scalar:
+            MU = _f64(MU.reshape(B, n))
+        sf = np.ascontiguousarray(np.broadcast_to(_vec(sf, n), (n,)))
+        mk = lambda *s: np.empty(s, dtype=np.float64)  # noqa: E731
+    res = out or {}
+    est = res.get("est") if res.get("est") is not None else mk(B, n)
+    se = (res.get("se") if res.get("se") is not None else mk(B, n)) if want_se else None
+    er = mk(B, n) if want_raw else None
+    sr = mk(B, n) if want_raw else None
+    info = mk(B, POST_INFO) if want_info else None
+    grid = mk(B, 600) if want_grid else None
+    h.check(h.lib.saver_cuda_calc_post(h.h, ptr(Y), ptr(MU), int(scalar), ptr(sf), n, B,
+                                       _D(float(scale_sf)), ptr(est), ptr(se), ptr(er), ptr(sr),
+                                       ptr(info), ptr(grid), int(dev)))
+    return dict(est=est, se=se, est_raw=er, se_raw=sr, info=info, grid=grid)
