@@ -527,7 +527,10 @@ static void fishnet1(int m, int p, const double *xs, const int *ju, const double
     double alf = 1.0;
     if (flmin < 1.0) {
         double eqs = flmin > eps ? flmin : eps;
-        alf = pow(eqs, 1.0 / (nlam - 1));
+        /* Fortran: alf=eqs**(1.0/(nlam-1)) -- the exponent is a REAL*4 expression.  Pinned by
+         * the golden lambda.min values (they sit on this grid to 1e-15, and 3e-9 off the
+         * double-precision-exponent grid). */
+        alf = pow(eqs, (double)(1.0f / (float)(nlam - 1)));
     }
     int nin = 0, nlp = 0, mnl = mnlam < nlam ? mnlam : nlam;
     const double shr = thr * dvr;

@@ -1,0 +1,114 @@
+"""Pin the CPU oracle against the reference's own golden object.
+
+The reference ships no unit tests; its only stored result is data/linnarsson_saver.rda
+(= saver(linnarsson), /root/reference/R/saver.R:75), committed as tests/golden/linnarsson.npz.
+"""
+import numpy as np
+
+import oracle
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - b) / np.abs(b)
+
+
+def test_t1_maxcor(golden):
+    G = golden["x"].shape[0]
+    mc = oracle.maxcor(golden["xest"], golden["y"], self_col=np.arange(G))
+    assert np.abs(mc - golden["maxcor"]).max() < 1e-12
+
+
+def test_t2_lambda_max_and_est_lambda(golden):
+    y, mc = golden["y"], golden["maxcor"]
+    n = y.shape[1]
+    pred = np.concatenate([golden["cv_genes"], golden["fixed_genes"]])
+    sd_n = y[pred].std(1)  # 1/n variance, glmnet's standardisation
+    assert _rel(mc[pred] * sd_n, golden["lambda_max"][pred]).max() < 1e-12
+    for g in golden["fixed_genes"][::25]:
+        lam = oracle.est_lambda(y[g], mc[g], golden["lambda_coefs"])
+        assert _rel(lam[0], golden["lambda_max"][g]) < 1e-12
+        assert _rel(lam[1], golden["lambda_min"][g]) < 1e-12
+    assert n == 200
+
+
+def test_t2b_lambda_regression(golden):
+    """lm(log(lambda.max/lambda.min)^2 ~ maxcor) over CV genes with maxcor > cutoff
+    (/root/reference/R/saver_fit.R:241-245) reproduces info$lambda.coefs."""
+    cv = golden["cv_genes"]
+    cv = cv[golden["maxcor"][cv] > golden["cutoff"][0]]
+    assert cv.size == 179
+    z = np.log(golden["lambda_max"][cv] / golden["lambda_min"][cv]) ** 2
+    A = np.stack([np.ones(cv.size), golden["maxcor"][cv]], 1)
+    coef = np.linalg.lstsq(A, z, rcond=None)[0]
+    assert np.abs(coef - golden["lambda_coefs"]).max() < 1e-10
+
+
+def test_t3_cv_lambda_grid(golden):
+    """glmnet's grid: lambda_k = lambda_max * alf^k with alf = 0.01^(REAL*4(1/99))."""
+    cv = golden["cv_genes"]
+    alf = 0.01 ** float(np.float32(1.0) / np.float32(99.0))
+    k = np.log(golden["lambda_min"][cv] / golden["lambda_max"][cv]) / np.log(alf)
+    assert np.abs(k - np.rint(k)).max() < 1e-9 and np.rint(k).max() <= 99
+
+
+def test_t4_null_genes_exact(golden):
+    ng = golden["null_genes"]
+    n = golden["x"].shape[1]
+    mu = np.repeat(golden["y"][ng].mean(1)[:, None], n, 1)
+    r = oracle.calc_post_batch(golden["x"][ng], mu, golden["sf"], 1.0)
+    fb = r["info"][:, 5] != 0
+    ok = (np.rint(r["est"] * 1000) == golden["estimate_m"][ng]).all(1) & \
+         (np.rint(r["se"] * 1000) == golden["se_m"][ng]).all(1)
+    assert (~fb).sum() == 760 and ok[~fb].all()
+    rel = _rel(r["est"][fb], golden["estimate_m"][ng][fb] / 1000.0)
+    assert np.median(rel) < 1e-3 and rel.max() < 1e-2  # expectation vs Monte-Carlo draw
+
+
+def _chosen_fallback(info):
+    return np.array([(int(i[5]) >> (1 if i[0] == 3 else int(i[0]))) & 1 for i in info], dtype=bool)
+
+
+def test_t5_fixed_lambda_chain(golden):
+    """est.lambda -> glmnet(lambda = seq) -> calc.post on fixed-lambda genes reproduces the
+    stored estimates digit for digit (glmnet's own thresh = 1e-7 iterate sequence)."""
+    sel = golden["fixed_genes"][::16]
+    r = oracle.predict_path_batch(golden["xest"], golden["y"][sel], golden["lambda_max"][sel],
+                                  golden["lambda_min"][sel], self_col=sel)
+    assert (r["rc"] == 0).all() and (r["jerr"] == 0).all()
+    pr = oracle.calc_post_batch(golden["x"][sel], r["mu"], golden["sf"], 1.0)
+    fb = _chosen_fallback(pr["info"])
+    exact = np.rint(pr["est"] * 1000) == golden["estimate_m"][sel]
+    assert exact[~fb].mean() > 0.99
+    gold = golden["estimate_m"][sel] / 1000.0
+    assert np.median(_rel(pr["est"], gold)[fb]) < 1e-3
+
+
+def test_t6_cv_genes_master_path(golden):
+    """Master path of cv.glmnet: lambda[1] == golden lambda.max, golden lambda.min is ON the
+    fitted grid, and mu at that lambda -> calc.post reproduces the stored estimates."""
+    sel = golden["cv_genes"][::8]
+    xest, y = golden["xest"], golden["y"]
+    for g in sel:
+        r = oracle.glmnet_poisson(xest, y[g], excl=int(g))
+        assert _rel(r["lam"][0], golden["lambda_max"][g]) < 1e-12
+        k = int(np.argmin(np.abs(np.log(r["lam"]) - np.log(golden["lambda_min"][g]))))
+        assert _rel(r["lam"][k], golden["lambda_min"][g]) < 1e-12
+        mu = np.exp(r["a0"][k] + xest.T @ r["beta"][k])
+        pr = oracle.calc_post(golden["x"][g], mu, golden["sf"])
+        if not _chosen_fallback(pr["info"][None])[0]:
+            assert (np.rint(pr["est"] * 1000) == golden["estimate_m"][g]).mean() > 0.99
+
+
+def test_cv_glue_runs_and_is_fold_dependent(golden):
+    g = int(golden["cv_genes"][0])
+    n = golden["x"].shape[1]
+    rng = np.random.default_rng(0)
+    outs = []
+    for _ in range(2):
+        fold = rng.permutation(np.arange(n) % 5 + 1)
+        r = oracle.predict_cv(golden["xest"], golden["y"][g], fold, excl=g)
+        assert r["rc"] == 0 and _rel(r["lambda_max"], golden["lambda_max"][g]) < 1e-12
+        assert r["lambda_min"] <= r["lambda_max"] and r["sd_cv"] >= 0
+        outs.append(r["idx"])
+    # golden lambda.min index is 12; random folds land in its neighbourhood
+    assert all(0 <= i <= 40 for i in outs)
