@@ -97,6 +97,18 @@ SAVER_API int saver_cuda_calc_post(saver_cuda_handle h, const double* Y, const d
                          double* est, double* se, double* est_raw, double* se_raw,
                          double* info, double* grid, int device_ptrs);
 
+/* ---- the shared design: x.est = t(log((x[good,] + 1) / sf)) of R/saver.R:156-157 ----
+ * xest: n x p column-major (n cells, p predictor genes).  Uploaded (or taken from the
+ * device), standardised once and kept resident in the handle until replaced/destroyed. */
+SAVER_API int saver_cuda_set_design(saver_cuda_handle h, const double* xest, int n, int p,
+                                    int device_ptrs);
+
+/* ---- calc.maxcor (R/calc_maxcor.R:26): out[g] = max_j |cor(x.est[, j], Y[, g])| ----
+ * Y: n x B (size-normalised expression, R/calc_estimate.R:75-77).  self_col[g] = 0-based
+ * column of x.est carrying the same gene name (zeroed pair), or -1; may be NULL. */
+SAVER_API int saver_cuda_maxcor(saver_cuda_handle h, const double* Y, int B, const int* self_col,
+                                double* out, int device_ptrs);
+
 #ifdef __cplusplus
 }
 #endif

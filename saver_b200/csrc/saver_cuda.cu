@@ -276,4 +276,48 @@ int saver_cuda_calc_post(saver_cuda_handle h, const double* Y, const double* MU,
   return SAVER_OK;
 }
 
+int saver_cuda_set_design(saver_cuda_handle h, const double* xest, int n, int p, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!xest || n < 2 || p < 1) return fail(h, SAVER_ERR_ARG, "set_design: bad arguments");
+  CU(cudaSetDevice(h->device));
+  InArr<double> dX;
+  CU(dX.bind(xest, (size_t)n * p, device_ptrs != 0, h->stream));
+  CU(h->design.build(dX.d, n, p, h->stream));
+  h->launches += 1;
+  CU(cudaStreamSynchronize(h->stream));
+  return SAVER_OK;
+}
+
+int saver_cuda_maxcor(saver_cuda_handle h, const double* Y, int B, const int* self_col,
+                      double* out, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!h->design.Xs) return fail(h, SAVER_ERR_STATE, "maxcor: call saver_cuda_set_design first");
+  if (!Y || !out || B < 0) return fail(h, SAVER_ERR_ARG, "maxcor: bad arguments");
+  if (B == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  const DesignState& D = h->design;
+  InArr<double> dY;
+  InArr<int> dSelf;
+  OutArr<double> dOut;
+  CU(dY.bind(Y, (size_t)D.n * B, dev, s));
+  CU(dSelf.bind(self_col, B, dev, s));
+  CU(dOut.bind(out, B, dev, s));
+  const int chunk = 1024;
+  DevBuf<double> R, Cm;
+  CU(R.alloc((size_t)D.ldx * chunk, s));
+  CU(Cm.alloc((size_t)D.p_pad * chunk, s));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    CU(launch_center_scale(dY.d + (size_t)b0 * D.n, D.n, D.ldx, nb, R.p, s));
+    CU(launch_gemm_tn_f64(D.Xs, D.ldx, R.p, D.ldx, Cm.p, D.p_pad, D.p, nb, D.ldx, s));
+    CU(launch_colmax(Cm.p, D.p_pad, D.p, nb, dSelf.d ? dSelf.d + b0 : nullptr, dOut.d + b0, s));
+    h->launches += 3;
+  }
+  CU(dOut.fetch(s));
+  if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}
+
 }  // extern "C"

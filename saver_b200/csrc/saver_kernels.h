@@ -34,15 +34,26 @@ struct LogLikArgs {
 // The shared design: x.est of R/saver.R:156-157, standardised once over all cells.
 struct DesignState {
   int n = 0, p = 0;
-  double* Xs = nullptr;     // n x p column-major, (x - mean) / sd_n  (sd with 1/n); constant columns -> 0
+  int ldx = 0;              // leading dimension (rows) of Xs: n rounded up to 16, zero padded
+  int p_pad = 0;            // allocated columns: p rounded up to 128
+  double* Xs = nullptr;     // ldx x p_pad column-major, (x - mean) / sd_n (1/n variance); constant columns -> 0
+  double* Xs2 = nullptr;    // Xs squared elementwise (per-fit second moments come from one GEMM)
   double* xmean = nullptr;  // p
   double* xsd = nullptr;    // p (0 marks a constant column)
+  cudaError_t build(const double* X_dev, int n, int p, cudaStream_t s);
   void release() {
-    cudaFree(Xs); cudaFree(xmean); cudaFree(xsd);
-    Xs = xmean = xsd = nullptr;
-    n = p = 0;
+    cudaFree(Xs); cudaFree(Xs2); cudaFree(xmean); cudaFree(xsd);
+    Xs = Xs2 = xmean = xsd = nullptr;
+    n = p = ldx = p_pad = 0;
   }
 };
+
+// C[M x N] (ldc) = A^T B; A: Kp x M (lda), B: Kp x N (ldb), column-major, see gemm64.cu
+cudaError_t launch_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, double* C,
+                               int ldc, int M, int N, int Kp, cudaStream_t stream);
+cudaError_t launch_center_scale(const double* Y, int n, int ldr, int B, double* R, cudaStream_t s);
+cudaError_t launch_colmax(const double* C, int ldc, int p, int B, const int* self, double* out,
+                          cudaStream_t s);
 
 size_t calc_post_smem_bytes(int n, int* stage);
 cudaError_t launch_calc_post(const CalcPostArgs& A, cudaStream_t stream);

@@ -89,3 +89,34 @@ def calc_post(Y, MU, sf, scale_sf=1.0, want_se=True, want_raw=False, want_info=T
                                        _D(float(scale_sf)), ptr(est), ptr(se), ptr(er), ptr(sr),
                                        ptr(info), ptr(grid), int(dev)))
     return dict(est=est, se=se, est_raw=er, se_raw=sr, info=info, grid=grid)
+
+
+def set_design(xest, handle=None):
+    """Install x.est (R/saver.R:156-157).  xest: (p, n) gene-major == n x p column-major."""
+    h = handle or default_handle()
+    dev = is_device(xest)
+    if not dev:
+        xest = _f64(xest)
+    p, n = xest.shape
+    h.check(h.lib.saver_cuda_set_design(h.h, ptr(xest), n, p, int(dev)))
+    h.design_shape = (n, p)
+
+
+def maxcor(Y, self_col=None, handle=None):
+    """calc.maxcor(x.est, t(y)) (R/calc_maxcor.R:26).  Y: (B, n); self_col: (B,) or None."""
+    h = handle or default_handle()
+    dev = is_device(Y)
+    if dev:
+        import torch
+        B, n = Y.shape
+        out = torch.empty(B, dtype=torch.float64, device=Y.device)
+        sc = self_col
+    else:
+        Y = _f64(np.atleast_2d(Y))
+        B, n = Y.shape
+        out = np.empty(B)
+        sc = None if self_col is None else np.ascontiguousarray(self_col, dtype=np.int32)
+    if n != h.design_shape[0]:
+        raise ValueError("Y has %d cells, design has %d" % (n, h.design_shape[0]))
+    h.check(h.lib.saver_cuda_maxcor(h.h, ptr(Y), B, ptr(sc), ptr(out), int(dev)))
+    return out
