@@ -109,6 +109,36 @@ SAVER_API int saver_cuda_set_design(saver_cuda_handle h, const double* xest, int
 SAVER_API int saver_cuda_maxcor(saver_cuda_handle h, const double* Y, int B, const int* self_col,
                                 double* out, int device_ptrs);
 
+/* ---- expr.predict, CV variant (R/expr_predict.R:39-60) for a panel of B genes ----
+ * = cv.glmnet(x.est[pred.cells, -self], y[pred.cells], family = "poisson", dfmax, nfolds),
+ * predict(s = "lambda.min", type = "response") for ALL cells.
+ * Y: n x B size-normalised expression.  foldid: n x B ints, 0 = cell is not a pred cell,
+ * 1..nfolds = the fold cv.glmnet drew for that cell (the R host draws it: set.seed(seed);
+ * sample(rep(seq(nfolds), length = N)), R/expr_predict.R:35-36 + cv.glmnet).  self_col as in
+ * maxcor.  mu: n x B.  fit4: 4 x B = lambda.max, lambda.min, sd.cv, 0-based index of lambda.min.
+ * status[B]: 0 ok; 1 sd(y) == 0 (mu = mean, R/expr_predict.R:37-38); 2 the fit failed and mu is
+ * the mean over pred cells with lambda.max = lambda.min = sd.cv = 0 (R/expr_predict.R:44-52).
+ * stats (optional) 4 x B ints: master path length, glmnet jerr, CD sweeps, gradient rounds.
+ * cvout (optional) 3 x 128 x B: lambda, cvm, cvsd of cv.glmnet (NaN beyond the path). */
+SAVER_API int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int* self_col,
+                                    const int* foldid, int nfolds, int dfmax, int nlambda,
+                                    double thresh, double* mu, double* fit4, int* status,
+                                    int* stats, double* cvout, int device_ptrs);
+
+/* ---- expr.predict, fixed-lambda variant (R/expr_predict.R:61-82) ----
+ * glmnet(lambda = c(exp(seq(log(lmax), log(lmin), by = -0.2)), lmin)), mu at s = lmin.
+ * pred_mask: n ints (non-zero = pred cell) or NULL for all cells.  lambda_max / lambda_min:
+ * HOST arrays of B values from est.lambda (R/utils.R:129-134) whatever device_ptrs says. */
+SAVER_API int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B,
+                                      const int* self_col, const int* pred_mask,
+                                      const double* lambda_max, const double* lambda_min,
+                                      int dfmax, double thresh, double* mu, int* status,
+                                      int* stats, int device_ptrs);
+
+/* Problem columns pushed through the gradient GEMM so far (roofline accounting in bench.py):
+ * every column is one 2 * n * p flop contraction against the resident design. */
+SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);
+
 #ifdef __cplusplus
 }
 #endif

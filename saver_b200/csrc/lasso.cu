@@ -1,0 +1,1013 @@
+// lasso.cu -- batched cross-validated Poisson lasso paths on one shared design.
+//
+// Replaces (reference file:line):
+//   R/expr_predict.R:39-60   expr.predict, CV variant   = glmnet::cv.glmnet(family="poisson",
+//                            dfmax=300, nfolds=5), s = "lambda.min"
+//   R/expr_predict.R:61-82   expr.predict, fixed-lambda variant = glmnet::glmnet(lambda=seq)
+// glmnet itself is not in the reference tree; its dense Poisson path (Fortran fishnet1) and the
+// cv.glmnet glue are restated in oracle/saver_oracle.c, which is what this
+// file is checked against.
+//
+// Formulation.  Every (gene, fit) pair -- fit 0 = master fit on all pred cells, fit f = fold f
+// held out -- is one "problem" with the SAME resident design Xs (cells x predictors, standardised
+// once over all cells).  A fit's own standardisation (glmnet standardises per fit, with that
+// fit's observation weights) is an affine map of Xs columns: x~ = (Xs - xm) * xi with per-fit
+// moments xm, xi that come out of two GEMMs against the 0/1 fold-weight panel.  Held-out rows
+// carry weight 0, so X is never row-compacted.
+//
+// Work split per lambda step of a problem:
+//   * everything that touches only the strong set (IRLS re-linearisation, cyclic coordinate
+//     descent, intercept) runs inside ONE CTA per problem with the working weights / residual
+//     staged in shared memory (lasso_round_kernel);
+//   * the full gradient X^T r over all p predictors -- glmnet's KKT check + strong rule, the
+//     O(n p) part -- is batched over all live problems into one FP64 DMMA GEMM (gemm64.cu).
+// A "round" = one GEMM + one round kernel; a problem advances one lambda (or repairs one KKT
+// violation) per round.  Finished problems leave the panel, so the GEMM shrinks with them.
+#include "lasso.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "saver_kernels.h"
+
+namespace saver {
+
+void LassoWs::release() {
+  if (base) cudaFree(base);
+  if (h_counter) cudaFreeHost(h_counter);
+  base = nullptr;
+  h_counter = nullptr;
+  cap_bytes = 0;
+}
+
+namespace {
+
+constexpr double kBig = 9.9e35, kSml = 1.0e-4 /* fdev 1e-5 x 10 */, kDevMax = 0.999;
+constexpr int kMnLam = 5;
+constexpr double kVarTiny = 1e-12;  // per-fit variance of a unit-variance column below this = constant
+
+struct RoundArgs {
+  const double* Xs;
+  const double* xsd;
+  int n, ldx, p, p_pad, P;
+  LassoParams prm;
+  const double* Yn;   // n x B (ld = n) normalised expression
+  const int* fold;    // n x B: 0 = not a pred cell, 1..nfolds (path variant: any non-zero)
+  const int* self;    // B or null
+  LassoWs ws;
+};
+
+// ---------------------------------------------------------------------------------------------
+// block reductions: every thread receives bit-identical totals (butterfly sums commute), so all
+// scalar control flow below is uniform across the CTA without broadcasts.  One __syncthreads per
+// call; `buf` holds 2 x 4 x 32 doubles and alternates so back-to-back calls do not race.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void bsum(double (&v)[K], double* buf, int& phase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* b = buf + phase * 128;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v[k] = warp_sum(v[k]);
+    if (lane == 0) b[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(lane < nw ? b[k * 32 + lane] : 0.0);
+  phase ^= 1;
+}
+
+__device__ __forceinline__ double bmax(double v, double* buf, int& phase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* b = buf + phase * 128;
+  v = warp_max(v);
+  if (lane == 0) b[warp] = v;
+  __syncthreads();
+  v = warp_max(lane < nw ? b[lane] : -INFINITY);
+  phase ^= 1;
+  return v;
+}
+
+__device__ __forceinline__ double2 ldg2(const double* p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup: per problem, observation weights (into the R panel, for the moment GEMMs) and the
+// null-model constants of fishnet1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lasso_setup_kernel(RoundArgs A) {
+  __shared__ double red[256];
+  int phase = 0;
+  const int pid = blockIdx.x, tid = threadIdx.x;
+  const int NF = A.prm.NF, g = pid / NF, fit = pid % NF, n = A.n;
+  const double* y = A.Yn + (size_t)g * n;
+  const int* fo = A.fold + (size_t)g * n;
+  double cnt = 0, cnth = 0, sy = 0, lo = INFINITY, hi = -INFINITY;
+  for (int i = tid; i < n; i += 256) {
+    const int f = fo[i];
+    const double yi = y[i];
+    lo = fmin(lo, yi);
+    hi = fmax(hi, yi);
+    const bool pred = f != 0;
+    if (pred && f != fit) { cnt += 1; sy += yi; }
+    if (pred && fit > 0 && f == fit) cnth += 1;
+  }
+  double v3[3] = {cnt, cnth, sy};
+  bsum<3>(v3, red, phase);
+  lo = -bmax(-lo, red, phase);
+  hi = bmax(hi, red, phase);
+  const int mtrain = (int)v3[0];
+  const double qv = mtrain > 0 ? 1.0 / mtrain : 0.0;
+  double yb = 0, tly = 0;
+  double* q = A.ws.R + (size_t)pid * A.ldx;
+  for (int i = tid; i < A.ldx; i += 256) {
+    double qi = 0;
+    if (i < n) {
+      const int f = fo[i];
+      if (f != 0 && f != fit) {
+        qi = qv;
+        const double t = qv * y[i];
+        yb += t;
+        if (t > 0) tly += t * log(y[i]);
+      }
+    }
+    q[i] = qi;
+  }
+  double v2[2] = {yb, tly};
+  bsum<2>(v2, red, phase);
+  yb = v2[0];
+  tly = v2[1];
+  if (tid == 0) {
+    LassoProb pr;
+    pr.gene = g; pr.fit = fit; pr.state = ST_INIT; pr.lidx = 0; pr.lmu = 0; pr.nin = 0; pr.nS = 0;
+    pr.jerr = 0; pr.nlp = 0; pr.ngrad = 0; pr.mtrain = mtrain; pr.slot = pid;
+    pr.al = 0; pr.al0 = 0; pr.qv = qv; pr.yb = yb;
+    pr.az = 0; pr.dv0 = 0; pr.dvr = 0; pr.shr = 0; pr.v0 = yb; pr.sumr = 0;
+    pr.cur_dev = 0; pr.cur_cv = 0; pr.ncv = v3[1];
+    bool neg = lo < 0.0;
+    if (mtrain < 1 || !(yb > 0.0) || neg) {
+      pr.jerr = neg ? 8888 : 9999;  // fishnet: negative response / no positive response
+      pr.state = ST_DONE;
+    } else {
+      pr.az = log(yb);
+      pr.dv0 = yb * (pr.az - 1.0);
+      pr.dvr = -yb + tly - pr.dv0;
+      pr.shr = A.prm.thr * pr.dvr;
+      if (!(pr.dvr > 0.0)) { pr.jerr = 7777; pr.state = ST_DONE; }  // constant response in this fit
+    }
+    A.ws.prob[pid] = pr;
+    if (fit == 0) {
+      A.ws.gstat[g] = (lo == hi) ? 1 : 0;  // sd(y) == 0 over ALL cells (R/expr_predict.R:37)
+      A.ws.gmean[g] = mtrain > 0 ? v3[2] / mtrain : 0.0;
+    }
+  }
+}
+
+// XM (= Xs^T q) and XI (= (Xs^2)^T q) -> per-fit mean and 1/sd; eligibility (glmnet ju + the
+// gene's own column, R/calc_estimate.R:103-110); clears the strong/active marks.
+__global__ void __launch_bounds__(256) lasso_moments_kernel(RoundArgs A) {
+  const int j = blockIdx.x * 256 + threadIdx.x, pid = blockIdx.y;
+  if (j >= A.p_pad) return;
+  const size_t o = (size_t)pid * A.p_pad + j;
+  const int g = pid / A.prm.NF;
+  double xi = 0.0;
+  if (j < A.p) {
+    const double m = A.ws.XM[o];
+    const double s2 = A.ws.XI[o] - m * m;
+    const int self = A.self ? A.self[g] : -1;
+    if (A.xsd[j] > 0.0 && j != self && s2 > kVarTiny) xi = 1.0 / sqrt(s2);
+  }
+  A.ws.XI[o] = xi;
+  A.ws.MM[o] = 0;
+}
+
+// null-model working weights / residual (fishnet1 prologue) -> W, WR and the GEMM panel R
+__global__ void __launch_bounds__(256) lasso_resid0_kernel(RoundArgs A) {
+  __shared__ double red[256];
+  int phase = 0;
+  const int pid = blockIdx.x, tid = threadIdx.x, n = A.n, ldx = A.ldx;
+  LassoProb* PR = A.ws.prob + pid;
+  const int g = PR->gene, fit = PR->fit;
+  const bool dead = PR->state == ST_DONE;
+  const double qv = PR->qv, yb = PR->yb, az = PR->az;
+  const double* y = A.Yn + (size_t)g * n;
+  const int* fo = A.fold + (size_t)g * n;
+  double* w = A.ws.W + (size_t)pid * ldx;
+  double* wr = A.ws.WR + (size_t)pid * ldx;
+  double* r = A.ws.R + (size_t)pid * ldx;
+  double sr = 0, tf = 0;
+  for (int i = tid; i < ldx; i += 256) {
+    double wi = 0, ri = 0;
+    if (i < n && !dead) {
+      const int f = fo[i];
+      if (f != 0 && f != fit) {
+        const double t = qv * y[i];
+        wi = qv * yb;
+        ri = t - wi;
+        tf += t * az;
+      }
+    }
+    w[i] = wi;
+    wr[i] = ri;
+    r[i] = ri;
+    sr += ri;
+  }
+  double v2[2] = {sr, tf};
+  bsum<2>(v2, red, phase);
+  if (tid == 0) {
+    PR->sumr = v2[0];
+    if (!dead) {
+      PR->cur_dev = (v2[1] - PR->v0 - PR->dv0) / PR->dvr;
+      const int pos = atomicAdd(A.ws.counters, 1);
+      A.ws.list0[pos] = pid;
+    }
+  }
+}
+
+// glmnet's automatic lambda sequence of the master fit (one CTA per gene); the folds run the same
+// values as a user sequence (cv.glmnet passes lambda = master$lambda, whose first entry has been
+// replaced by exp(2 log l2 - log l3), glmnet's fix.lam).
+__global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
+  __shared__ double red[256];
+  int phase = 0;
+  const int g = blockIdx.x, tid = threadIdx.x, pid = g * A.prm.NF;
+  const LassoProb* PR = A.ws.prob + pid;
+  const double sumr = PR->sumr;
+  const double* Gc = A.ws.G + (size_t)PR->slot * A.p_pad;
+  const double* XMc = A.ws.XM + (size_t)pid * A.p_pad;
+  const double* XIc = A.ws.XI + (size_t)pid * A.p_pad;
+  double m = 0.0;
+  for (int j = tid; j < A.p; j += 256) {
+    const double xi = XIc[j];
+    if (xi != 0.0) m = fmax(m, fabs((Gc[j] - XMc[j] * sumr) * xi));
+  }
+  m = bmax(m, red, phase);
+  if (tid == 0) {
+    const int self = A.self ? A.self[g] : -1;
+    const int nvars = A.p - (self >= 0 ? 1 : 0);
+    const double alf = PR->mtrain < nvars ? A.prm.alf_wide : A.prm.alf_tall;
+    double* lam = A.ws.lam + (size_t)g * kNLam;
+    const int nlam = A.prm.nlam;
+    lam[0] = kBig;
+    double al = m;
+    for (int l = 1; l < nlam; ++l) {
+      al *= alf;
+      lam[l] = al;
+    }
+    if (nlam > 2) lam[0] = exp(2.0 * log(lam[1]) - log(lam[2]));
+    A.ws.nlam_g[g] = nlam;
+    A.ws.Lfinal[g] = nlam;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the round kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kFixedSmem = 256 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4;
+
+template <int T>
+__device__ __forceinline__ int rebuild_strong(const int* MMc, int* SIc, int p, int* ish) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  int base = 0;
+  for (int j0 = 0; j0 < p; j0 += T) {
+    const int j = j0 + tid;
+    const bool flag = j < p && MMc[j] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) ish[warp] = __popc(b);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+      const int c = ish[w];
+      if (w < warp) woff += c;
+      tot += c;
+    }
+    if (flag) SIc[base + woff + __popc(b & ((1u << lane) - 1u))] = j;
+    base += tot;
+    __syncthreads();
+  }
+  return base;
+}
+
+template <int T, bool STAGED>
+__global__ void __launch_bounds__(T)
+lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ nextlist,
+                   int* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* red = reinterpret_cast<double*>(smraw);
+  double* aact = red + 256;
+  double* as_ = aact + kNX;
+  double* va = as_ + kNX;
+  double* swa = va + kNX;
+  double* xma = swa + kNX;
+  double* xia = xma + kNX;
+  int* ia = reinterpret_cast<int*>(xia + kNX);
+  int* ish = ia + kNX;
+  double* wv = reinterpret_cast<double*>(ish + 64);
+  double* wrv = wv + A.ldx;
+
+  const int tid = threadIdx.x;
+  int phase = 0;
+  const int pid = list[blockIdx.x];
+  LassoProb* PR = A.ws.prob + pid;
+  const int g = PR->gene, fit = PR->fit, slot = PR->slot;
+  int state = PR->state, lidx = PR->lidx, lmu = PR->lmu, nin = PR->nin, nS = PR->nS;
+  int jerr = PR->jerr, nlp = PR->nlp;
+  double al = PR->al, al0 = PR->al0, az = PR->az, v0 = PR->v0, sumr = PR->sumr;
+  double cur_dev = PR->cur_dev, cur_cv = PR->cur_cv;
+  const double qv = PR->qv, dv0 = PR->dv0, dvr = PR->dvr, shr = PR->shr, ncv = PR->ncv;
+  const int n = A.n, ldx = A.ldx, p = A.p, p_pad = A.p_pad;
+  const double* __restrict__ Xs = A.Xs;
+  const double* Gc = A.ws.G + (size_t)slot * p_pad;
+  const double* XMc = A.ws.XM + (size_t)pid * p_pad;
+  const double* XIc = A.ws.XI + (size_t)pid * p_pad;
+  int* MMc = A.ws.MM + (size_t)pid * p_pad;
+  int* SIc = A.ws.SIDX + (size_t)pid * p_pad;
+  int* IAg = A.ws.IA + (size_t)pid * kNX;
+  double* AAg = A.ws.AACT + (size_t)pid * kNX;
+  double* Wg = A.ws.W + (size_t)pid * ldx;
+  double* WRg = A.ws.WR + (size_t)pid * ldx;
+  const double* y = A.Yn + (size_t)g * n;
+  const int* fo = A.fold + (size_t)g * n;
+  const int self = A.self ? A.self[g] : -1;
+  const int nvars = p - (self >= 0 ? 1 : 0);
+  int nx = 2 * A.prm.dfmax + 20;
+  if (nx > nvars) nx = nvars;
+  if (nx > kNX) nx = kNX;
+  const int ne = A.prm.dfmax;
+  const int nlam = A.ws.nlam_g[g];
+  const double* lamg = A.ws.lam + (size_t)g * kNLam;
+  const bool master_auto = A.prm.auto_lambda && fit == 0;
+  const bool is_fold = fit > 0;
+  const int maxit = A.prm.maxit;
+  const double fmax_ = log(DBL_MAX * 0.1);
+
+  if (!STAGED) {
+    wv = Wg;
+    wrv = WRg;
+  } else {
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      *reinterpret_cast<double2*>(wv + i) = *reinterpret_cast<const double2*>(Wg + i);
+      *reinterpret_cast<double2*>(wrv + i) = *reinterpret_cast<const double2*>(WRg + i);
+    }
+  }
+  for (int l = tid; l < nin; l += T) {
+    const int k = IAg[l];
+    ia[l] = k;
+    aact[l] = AAg[l];
+    xma[l] = XMc[k];
+    xia[l] = XIc[k];
+  }
+  __syncthreads();
+
+  // ---------------- phase A: consume the gradient of the previous round ----------------
+  auto mark_pass = [&](double thresh) -> int {
+    int cnt = 0;
+    for (int j = tid; j < p; j += T) {
+      const double xi = XIc[j];
+      if (xi != 0.0 && MMc[j] == 0) {
+        const double ga = fabs((Gc[j] - XMc[j] * sumr) * xi);
+        if (ga > thresh) {
+          MMc[j] = -1;
+          ++cnt;
+        }
+      }
+    }
+    return __syncthreads_or(cnt);
+  };
+
+  bool strong_changed = false;
+  if (state == ST_INIT && (nlam < 1 || A.ws.prob[(size_t)g * A.prm.NF].jerr > 0)) {
+    state = ST_DONE;  // the gene's master fit failed: the whole gene falls back to the mean
+  } else if (state == ST_INIT) {
+    if (master_auto) {
+      double m = 0.0;
+      for (int j = tid; j < p; j += T) {
+        const double xi = XIc[j];
+        if (xi != 0.0) m = fmax(m, fabs((Gc[j] - XMc[j] * sumr) * xi));
+      }
+      m = bmax(m, red, phase);
+      if (tid == 0) {  // the null model is solution 0 (lambda = "big")
+        A.ws.a0p[(size_t)g * kNLam] = az;
+        A.ws.devp[(size_t)g * kNLam] = cur_dev;
+        A.ws.ninp[(size_t)g * kNLam] = 0;
+      }
+      lmu = 1;
+      lidx = 1;
+      al0 = m;
+      al = lamg[1];
+      if (nlam < 2) state = ST_DONE;
+    } else {
+      lidx = 0;
+      al0 = 0.0;
+      al = lamg[0];
+    }
+    if (state != ST_DONE) {
+      strong_changed = mark_pass(2.0 * al - al0) != 0;
+      state = ST_SOLVE;
+    }
+  } else if (state == ST_WAIT_KKT) {
+    if (mark_pass(al)) {
+      strong_changed = true;
+      state = ST_SOLVE;  // KKT violated outside the strong set: re-solve this lambda
+    } else {
+      // ---- commit solution lidx ----
+      if (fit == 0) {
+        const size_t o = (size_t)g * kNLam + lidx;
+        if (tid == 0) {
+          A.ws.a0p[o] = az;
+          A.ws.devp[o] = cur_dev;
+          A.ws.ninp[o] = nin;
+        }
+        double* cp = A.ws.cap + o * kNX;
+        for (int l = tid; l < nin; l += T) cp[l] = aact[l];
+      } else if (tid == 0) {
+        A.ws.cvdev[((size_t)g * kNLam + lidx) * kMaxFolds + (fit - 1)] = cur_cv / ncv;
+      }
+      lmu = lidx + 1;
+      bool stop = false;
+      if (master_auto) {
+        const int mnl = kMnLam < nlam ? kMnLam : nlam;
+        if (lidx + 1 >= mnl) {
+          int me = 0;
+          for (int l = tid; l < nin; l += T) me += aact[l] != 0.0;
+          double mv[1] = {(double)me};
+          bsum<1>(mv, red, phase);
+          const double dprev = A.ws.devp[(size_t)g * kNLam + lidx - mnl + 1];
+          if (mv[0] > ne) stop = true;
+          else if ((cur_dev - dprev) / cur_dev < kSml) stop = true;
+          else if (cur_dev > kDevMax) stop = true;
+        }
+      }
+      int lim = nlam;
+      if (is_fold && A.prm.auto_lambda) {
+        const int lf = *reinterpret_cast<volatile int*>(A.ws.Lfinal + g);
+        if (lf < lim) lim = lf;
+      }
+      if (stop || lidx + 1 >= lim) {
+        state = ST_DONE;
+      } else {
+        ++lidx;
+        al0 = al;
+        al = lamg[lidx];
+        strong_changed = mark_pass(2.0 * al - al0) != 0;
+        state = ST_SOLVE;
+      }
+    }
+  }
+  if (strong_changed) nS = rebuild_strong<T>(MMc, SIc, p, ish);
+
+  // ---------------- phase B: IRLS + coordinate descent on the strong set ----------------
+  auto intercept_update = [&](double& dlx) {
+    double s[1] = {0.0};
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+      s[0] += r.x + r.y;
+    }
+    bsum<1>(s, red, phase);
+    const double d = s[0] / v0;
+    az += d;
+    dlx = fmax(dlx, v0 * d * d);
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      double2 r = *reinterpret_cast<const double2*>(wrv + i);
+      const double2 w = *reinterpret_cast<const double2*>(wv + i);
+      r.x -= d * w.x;
+      r.y -= d * w.y;
+      *reinterpret_cast<double2*>(wrv + i) = r;
+    }
+    sumr = s[0] - d * v0;
+  };
+  auto axpy = [&](const double* col, double d, double xm, double xi) {
+    const double c = d * xi;
+#pragma unroll 2
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      const double2 x = ldg2(col + i);
+      double2 r = *reinterpret_cast<const double2*>(wrv + i);
+      const double2 w = *reinterpret_cast<const double2*>(wv + i);
+      r.x -= c * w.x * (x.x - xm);
+      r.y -= c * w.y * (x.y - xm);
+      *reinterpret_cast<double2*>(wrv + i) = r;
+    }
+  };
+
+  if (state == ST_SOLVE) {
+    while (true) {  // IRLS iterations
+      const double az0 = az;
+      for (int l = tid; l < nin; l += T) as_[l] = aact[l];
+      bool overflow = false, maxed = false, nanfail = false;
+      while (true) {  // sweeps over the strong set until one changes nothing
+        ++nlp;
+        double dlx = 0.0;
+        if (nS > 0 && (tid & 7) == 0) {
+          const double* c0 = Xs + (size_t)SIc[0] * ldx;
+          for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(c0 + i);
+        }
+        for (int s = 0; s < nS; ++s) {
+          const int k = SIc[s];
+          const double* col = Xs + (size_t)k * ldx;
+          if (s + 1 < nS && (tid & 7) == 0) {
+            const double* cn = Xs + (size_t)SIc[s + 1] * ldx;
+            for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(cn + i);
+          }
+          int pos = MMc[k];
+          const double xm = XMc[k], xi = XIc[k];
+          const double ak = pos > 0 ? aact[pos - 1] : 0.0;  // read before the reduction's barrier
+          double d3[3] = {0.0, 0.0, 0.0};
+#pragma unroll 2
+          for (int i = 2 * tid; i < ldx; i += 2 * T) {
+            const double2 x = ldg2(col + i);
+            const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+            const double2 w = *reinterpret_cast<const double2*>(wv + i);
+            d3[0] += r.x * x.x + r.y * x.y;
+            const double wx0 = w.x * x.x, wx1 = w.y * x.y;
+            d3[1] += wx0 + wx1;
+            d3[2] += wx0 * x.x + wx1 * x.y;
+          }
+          bsum<3>(d3, red, phase);
+          const double sw = xi * (d3[1] - xm * v0);
+          const double v = xi * xi * (d3[2] - 2.0 * xm * d3[1] + xm * xm * v0);
+          const double gk = xi * (d3[0] - xm * sumr);
+          const double u = gk + v * ak;
+          const double au = fabs(u) - al;
+          const double anew = au > 0.0 ? copysign(au, u) / v : 0.0;
+          if (pos > 0 && tid == 0) {
+            va[pos - 1] = v;
+            swa[pos - 1] = sw;
+          }
+          if (anew == ak) continue;
+          if (anew != anew) { nanfail = true; break; }
+          const double d = anew - ak;
+          dlx = fmax(dlx, v * d * d);
+          axpy(col, d, xm, xi);
+          sumr -= d * sw;
+          if (pos < 0) {
+            ++nin;
+            if (nin > nx) { overflow = true; break; }
+            pos = nin;
+            if (tid == 0) {
+              MMc[k] = nin;
+              ia[nin - 1] = k;
+              xma[nin - 1] = xm;
+              xia[nin - 1] = xi;
+              va[nin - 1] = v;
+              swa[nin - 1] = sw;
+              as_[nin - 1] = 0.0;
+            }
+          }
+          if (tid == 0) aact[pos - 1] = anew;
+          // aact / va are next read after at least one __syncthreads (the next bsum)
+        }
+        if (overflow || nanfail) break;
+        intercept_update(dlx);
+        if (dlx < shr) break;
+        if (!(dlx == dlx)) { nanfail = true; break; }
+        if (nlp > maxit) { maxed = true; break; }
+        while (true) {  // sweeps over the ever-active list
+          ++nlp;
+          dlx = 0.0;
+          for (int l = 0; l < nin; ++l) {
+            const int k = ia[l];
+            const double* col = Xs + (size_t)k * ldx;
+            if (l + 1 < nin && (tid & 7) == 0) {
+              const double* cn = Xs + (size_t)ia[l + 1] * ldx;
+              for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(cn + i);
+            }
+            const double xm = xma[l], xi = xia[l], v = va[l], ak = aact[l], sw = swa[l];
+            double d1[1] = {0.0};
+#pragma unroll 2
+            for (int i = 2 * tid; i < ldx; i += 2 * T) {
+              const double2 x = ldg2(col + i);
+              const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+              d1[0] += r.x * x.x + r.y * x.y;
+            }
+            bsum<1>(d1, red, phase);
+            const double gk = xi * (d1[0] - xm * sumr);
+            const double u = gk + v * ak;
+            const double au = fabs(u) - al;
+            const double anew = au > 0.0 ? copysign(au, u) / v : 0.0;
+            if (anew == ak) continue;
+            if (anew != anew) { nanfail = true; break; }
+            const double d = anew - ak;
+            dlx = fmax(dlx, v * d * d);
+            axpy(col, d, xm, xi);
+            sumr -= d * sw;
+            if (tid == 0) aact[l] = anew;  // all reads of aact[l] precede the reduction's barrier
+          }
+          if (nanfail) break;
+          intercept_update(dlx);
+          if (dlx < shr) break;
+          if (!(dlx == dlx)) { nanfail = true; break; }
+          if (nlp > maxit) { maxed = true; break; }
+        }
+        if (maxed || nanfail) break;
+      }
+      if (overflow) { jerr = -10000 - (lidx + 1); state = ST_DONE; break; }
+      if (maxed) { jerr = -(lidx + 1); state = ST_DONE; break; }
+      if (nanfail) { jerr = 9998; state = ST_DONE; break; }
+
+      // ---- re-linearise: f = az + sum_l a_l x~_l, w = q exp(f), wr = t - w ----
+      __syncthreads();
+      double c0p[1] = {0.0};
+      for (int l = tid; l < nin; l += T) {
+        const double b = aact[l] * xia[l];
+        swa[l] = b;  // swa is dead until the next strong sweep recomputes it
+        c0p[0] += b * xma[l];
+      }
+      bsum<1>(c0p, red, phase);
+      const double c0 = az - c0p[0];
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum w, sum t f, sum wr, held-out deviance
+      for (int i = 2 * tid; i < ldx; i += 2 * T) {
+        double f0 = c0, f1 = c0;
+#pragma unroll 4
+        for (int l = 0; l < nin; ++l) {
+          const double b = swa[l];
+          if (b != 0.0) {
+            const double2 x = ldg2(Xs + (size_t)ia[l] * ldx + i);
+            f0 += b * x.x;
+            f1 += b * x.y;
+          }
+        }
+        double wn[2] = {0.0, 0.0}, rn[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ii = i + e;
+          if (ii < n) {
+            const int f = fo[ii];
+            const double fe = e ? f1 : f0;
+            if (f != 0 && f != fit) {
+              const double yi = y[ii];
+              const double t = qv * yi;
+              const double fc = fabs(fe) < fmax_ ? fe : copysign(fmax_, fe);
+              wn[e] = qv * exp(fc);
+              rn[e] = t - wn[e];
+              acc[0] += wn[e];
+              acc[1] += t * fe;
+              acc[2] += rn[e];
+            } else if (f != 0 && is_fold) {  // held-out row of this fold
+              const double yi = y[ii];
+              const double devy = yi == 0.0 ? 0.0 : yi * log(yi) - yi;
+              acc[3] += 2.0 * (devy - (yi * fe - exp(fe)));
+            }
+          }
+        }
+        *reinterpret_cast<double2*>(wv + i) = make_double2(wn[0], wn[1]);
+        *reinterpret_cast<double2*>(wrv + i) = make_double2(rn[0], rn[1]);
+      }
+      bsum<4>(acc, red, phase);
+      v0 = acc[0];
+      sumr = acc[2];
+      cur_dev = (acc[1] - v0 - dv0) / dvr;
+      cur_cv = acc[3];
+      // ---- outer convergence (fishnet1: intercept and every active coefficient) ----
+      int bad = v0 * (az - az0) * (az - az0) >= shr;
+      for (int l = tid; l < nin; l += T) {
+        const double d = aact[l] - as_[l];
+        bad |= va[l] * d * d >= shr;
+      }
+      if (!__syncthreads_or(bad)) {
+        state = ST_WAIT_KKT;
+        break;
+      }
+    }
+  }
+
+  // ---------------- write back ----------------
+  __syncthreads();
+  if (STAGED) {
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      *reinterpret_cast<double2*>(Wg + i) = *reinterpret_cast<const double2*>(wv + i);
+      *reinterpret_cast<double2*>(WRg + i) = *reinterpret_cast<const double2*>(wrv + i);
+    }
+  }
+  for (int l = tid; l < nin && l < kNX; l += T) {
+    IAg[l] = ia[l];
+    AAg[l] = aact[l];
+  }
+  if (state != ST_DONE) {
+    if (tid == 0) {
+      const int pos = atomicAdd(counter, 1);
+      nextlist[pos] = pid;
+      ish[40] = pos;
+    }
+    __syncthreads();
+    const int pos = ish[40];
+    double* r = A.ws.R + (size_t)pos * ldx;
+    for (int i = 2 * tid; i < ldx; i += 2 * T)
+      *reinterpret_cast<double2*>(r + i) = *reinterpret_cast<const double2*>(wrv + i);
+    if (tid == 0) PR->slot = pos;
+  }
+  if (tid == 0) {
+    if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
+    PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
+    PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
+    PR->al = al; PR->al0 = al0; PR->az = az; PR->v0 = v0; PR->sumr = sumr;
+    PR->cur_dev = cur_dev; PR->cur_cv = cur_cv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: cv.glmnet statistics + lambda.min + prediction for all cells (one CTA per gene)
+// ---------------------------------------------------------------------------------------------
+struct FinalArgs {
+  RoundArgs R;
+  const double* lmin_user;  // path variant: s = lambda.min per gene
+  double* MU;               // n x B
+  double* out4;             // 4 x B: lambda.max, lambda.min, sd.cv, index
+  int* status;              // B: 0 ok, 1 sd(y)==0, 2 fit failed (mean prediction)
+  int* stats;               // 4 x B: lmu, jerr, sweeps, gradient rounds (summed over fits)
+  double* cvout;            // optional 3 x kNLam x B: lambda, cvm, cvsd
+};
+
+__global__ void __launch_bounds__(256) lasso_finalize_kernel(FinalArgs F) {
+  __shared__ double cvm[kNLam], cvsd[kNLam], bco[kNX];
+  __shared__ int sh_i[4];
+  __shared__ double sh_d[4];
+  const RoundArgs& A = F.R;
+  const int g = blockIdx.x, tid = threadIdx.x, NF = A.prm.NF, n = A.n, ldx = A.ldx;
+  const LassoProb* P0 = A.ws.prob + (size_t)g * NF;
+  const double* lam = A.ws.lam + (size_t)g * kNLam;
+  double* mu = F.MU + (size_t)g * n;
+  int st = 0;
+  if (A.ws.gstat[g]) st = 1;
+  int L = P0->lmu;
+  if (!st) {
+    for (int f = 0; f < NF; ++f)
+      if (P0[f].jerr > 0 || P0[f].lmu < 1) st = 2;
+  }
+  if (F.stats && tid == 0) {
+    int nlp = 0, ngr = 0;
+    for (int f = 0; f < NF; ++f) { nlp += P0[f].nlp; ngr += P0[f].ngrad; }
+    F.stats[4 * g + 0] = L; F.stats[4 * g + 1] = P0->jerr; F.stats[4 * g + 2] = nlp; F.stats[4 * g + 3] = ngr;
+  }
+  if (st) {
+    const double m = A.ws.gmean[g];
+    for (int i = tid; i < n; i += 256) mu[i] = m;
+    if (tid == 0) {
+      F.out4[4 * g + 0] = 0; F.out4[4 * g + 1] = 0; F.out4[4 * g + 2] = 0; F.out4[4 * g + 3] = -1;
+      F.status[g] = st;
+    }
+    return;
+  }
+  int left, right;
+  double frac = 1.0;
+  if (A.prm.auto_lambda) {
+    const int nfolds = A.prm.nfolds;
+    for (int l = tid; l < L; l += 256) {
+      double wsum = 0, s = 0;
+      for (int f = 0; f < nfolds; ++f) {
+        const int lf = l < P0[f + 1].lmu ? l : P0[f + 1].lmu - 1;  // short fold path: last column
+        const double c = A.ws.cvdev[((size_t)g * kNLam + lf) * kMaxFolds + f];
+        s += P0[f + 1].ncv * c;
+        wsum += P0[f + 1].ncv;
+      }
+      const double m = s / wsum;
+      double s2 = 0;
+      for (int f = 0; f < nfolds; ++f) {
+        const int lf = l < P0[f + 1].lmu ? l : P0[f + 1].lmu - 1;
+        const double d = A.ws.cvdev[((size_t)g * kNLam + lf) * kMaxFolds + f] - m;
+        s2 += P0[f + 1].ncv * d * d;
+      }
+      cvm[l] = m;
+      cvsd[l] = sqrt(s2 / wsum / (nfolds - 1));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double best = INFINITY;
+      for (int l = 0; l < L; ++l) if (cvm[l] < best) best = cvm[l];
+      int imin = -1;
+      for (int l = 0; l < L; ++l) if (cvm[l] <= best) { imin = l; break; }  // largest lambda at the minimum
+      sh_i[0] = imin;
+      if (imin >= 0) {
+        F.out4[4 * g + 0] = lam[0];
+        F.out4[4 * g + 1] = lam[imin];
+        F.out4[4 * g + 2] = (cvm[0] - cvm[imin]) / cvsd[imin];
+        F.out4[4 * g + 3] = imin;
+      }
+    }
+    if (F.cvout) {
+      double* co = F.cvout + (size_t)g * 3 * kNLam;
+      for (int l = tid; l < kNLam; l += 256) {
+        co[l] = l < L ? lam[l] : NAN;
+        co[kNLam + l] = l < L ? cvm[l] : NAN;
+        co[2 * kNLam + l] = l < L ? cvsd[l] : NAN;
+      }
+    }
+    __syncthreads();
+    left = right = sh_i[0];
+    if (left < 0) {  // every cvm is NaN: cv.glmnet cannot pick -> treated as a failed fit
+      const double m = A.ws.gmean[g];
+      for (int i = tid; i < n; i += 256) mu[i] = m;
+      if (tid == 0) {
+        F.out4[4 * g + 0] = 0; F.out4[4 * g + 1] = 0; F.out4[4 * g + 2] = 0; F.out4[4 * g + 3] = -1;
+        F.status[g] = 2;
+      }
+      return;
+    }
+  } else {
+    // predict.glmnet(s = lambda.min): glmnet's lambda.interp on the fitted sequence
+    if (tid == 0) {
+      double s = F.lmin_user[g];
+      int lf = L - 1, rt = L - 1;
+      double fr = 1.0;
+      if (s > lam[0]) s = lam[0];
+      if (s < lam[L - 1]) s = lam[L - 1];
+      if (L > 1 && lam[0] > lam[L - 1]) {
+        const double den = lam[0] - lam[L - 1];
+        const double sfrac = (lam[0] - s) / den;
+        lf = 0;
+        rt = L - 1;
+        for (int l = 0; l < L; ++l) if ((lam[0] - lam[l]) / den <= sfrac) lf = l;
+        for (int l = L - 1; l >= 0; --l) if ((lam[0] - lam[l]) / den >= sfrac) rt = l;
+        fr = lam[lf] == lam[rt] ? 1.0 : (s - lam[rt]) / (lam[lf] - lam[rt]);
+      }
+      sh_i[0] = lf; sh_i[1] = rt; sh_d[0] = fr;
+      F.out4[4 * g + 0] = lam[0];
+      F.out4[4 * g + 1] = s;
+      F.out4[4 * g + 2] = NAN;
+      F.out4[4 * g + 3] = rt;
+    }
+    __syncthreads();
+    left = sh_i[0]; right = sh_i[1]; frac = sh_d[0];
+  }
+  // coefficients on the Xs scale: b_l = a_l * xi_l ; intercept shift sum b_l xm_l
+  const size_t oL = (size_t)g * kNLam + left, oR = (size_t)g * kNLam + right;
+  const int ninL = A.ws.ninp[oL], ninR = A.ws.ninp[oR];
+  const int nmax = ninL > ninR ? ninL : ninR;
+  const size_t pid0 = (size_t)g * NF;
+  const int* IAg = A.ws.IA + pid0 * kNX;
+  const double* XMc = A.ws.XM + pid0 * A.p_pad;
+  const double* XIc = A.ws.XI + pid0 * A.p_pad;
+  __shared__ double red[256];
+  int phase = 0;
+  double sh[1] = {0.0};
+  for (int l = tid; l < nmax; l += 256) {
+    const double aL = l < ninL ? A.ws.cap[oL * kNX + l] : 0.0;
+    const double aR = l < ninR ? A.ws.cap[oR * kNX + l] : 0.0;
+    const int k = IAg[l];
+    const double b = (frac * aL + (1.0 - frac) * aR) * XIc[k];
+    bco[l] = b;
+    sh[0] += b * XMc[k];
+  }
+  bsum<1>(sh, red, phase);
+  const double a0 = frac * A.ws.a0p[oL] + (1.0 - frac) * A.ws.a0p[oR] - sh[0];
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    double f = a0;
+    for (int l = 0; l < nmax; ++l) {
+      const double b = bco[l];
+      if (b != 0.0) f += b * __ldg(A.Xs + (size_t)IAg[l] * ldx + i);
+    }
+    mu[i] = exp(f);
+  }
+  if (tid == 0) F.status[g] = 0;
+}
+
+template <int T>
+cudaError_t launch_round_t(const RoundArgs& A, const int* list, int* nextlist, int* counter,
+                           int grid, bool staged, size_t smem, cudaStream_t s) {
+  cudaError_t e;
+  if (staged) {
+    e = cudaFuncSetAttribute(lasso_round_kernel<T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lasso_round_kernel<T, true><<<grid, T, smem, s>>>(A, list, nextlist, counter);
+  } else {
+    e = cudaFuncSetAttribute(lasso_round_kernel<T, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lasso_round_kernel<T, false><<<grid, T, smem, s>>>(A, list, nextlist, counter);
+  }
+  return cudaGetLastError();
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+int lasso_max_block(int NF) {
+  int b = 3072 / NF;
+  return b < 1 ? 1 : b;
+}
+
+// Runs one block of B genes.  All pointers are device pointers.
+cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm, const double* Yn,
+                      const int* fold, const int* self, const double* lam_user,
+                      const int* nlam_user, const double* lmin_user, double* MU, double* out4,
+                      int* status, int* stats, double* cvout, cudaStream_t s, long long* launches,
+                      long long* gemm_cols) {
+  const int B = prm.B, NF = prm.NF, P = B * NF;
+  if (B <= 0) return cudaSuccess;
+  const int n = D.n, ldx = D.ldx, p_pad = D.p_pad;
+  const int P_pad = (P + 63) / 64 * 64;
+  // ---- carve the workspace ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t oR = take((size_t)ldx * P_pad * 8), oW = take((size_t)ldx * P_pad * 8),
+               oWR = take((size_t)ldx * P_pad * 8), oG = take((size_t)p_pad * P_pad * 8),
+               oXM = take((size_t)p_pad * P_pad * 8), oXI = take((size_t)p_pad * P_pad * 8),
+               oMM = take((size_t)p_pad * P * 4), oSI = take((size_t)p_pad * P * 4),
+               oIA = take((size_t)kNX * P * 4), oAA = take((size_t)kNX * P * 8),
+               oPR = take(sizeof(LassoProb) * (size_t)P), oLam = take((size_t)kNLam * B * 8),
+               oNl = take((size_t)B * 4), oLf = take((size_t)B * 4), oGs = take((size_t)B * 4),
+               oGm = take((size_t)B * 8), oA0 = take((size_t)kNLam * B * 8),
+               oDv = take((size_t)kNLam * B * 8), oNi = take((size_t)kNLam * B * 4),
+               oCap = take((size_t)kNX * kNLam * B * 8),
+               oCv = take((size_t)kNLam * kMaxFolds * B * 8), oL0 = take((size_t)P * 4),
+               oL1 = take((size_t)P * 4), oCt = take(64);
+  cudaError_t e;
+  if (off > ws.cap_bytes) {
+    if (ws.base) {
+      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+      cudaFree(ws.base);
+      ws.base = nullptr;
+      ws.cap_bytes = 0;
+    }
+    if ((e = cudaMalloc(&ws.base, off)) != cudaSuccess) return e;
+    ws.cap_bytes = off;
+  }
+  if (!ws.h_counter && (e = cudaMallocHost(&ws.h_counter, 64)) != cudaSuccess) return e;
+  unsigned char* b = ws.base;
+  ws.R = (double*)(b + oR); ws.W = (double*)(b + oW); ws.WR = (double*)(b + oWR);
+  ws.G = (double*)(b + oG); ws.XM = (double*)(b + oXM); ws.XI = (double*)(b + oXI);
+  ws.MM = (int*)(b + oMM); ws.SIDX = (int*)(b + oSI); ws.IA = (int*)(b + oIA);
+  ws.AACT = (double*)(b + oAA); ws.prob = (LassoProb*)(b + oPR); ws.lam = (double*)(b + oLam);
+  ws.nlam_g = (int*)(b + oNl); ws.Lfinal = (int*)(b + oLf); ws.gstat = (int*)(b + oGs);
+  ws.gmean = (double*)(b + oGm); ws.a0p = (double*)(b + oA0); ws.devp = (double*)(b + oDv);
+  ws.ninp = (int*)(b + oNi); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
+  ws.list0 = (int*)(b + oL0); ws.list1 = (int*)(b + oL1); ws.counters = (int*)(b + oCt);
+
+  RoundArgs A;
+  A.Xs = D.Xs; A.xsd = D.xsd; A.n = n; A.ldx = ldx; A.p = D.p; A.p_pad = p_pad; A.P = P;
+  A.prm = prm; A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
+
+  if ((e = cudaMemsetAsync(ws.counters, 0, 64, s)) != cudaSuccess) return e;
+  // the padding columns of the GEMM panel must hold finite numbers
+  if (P_pad > P &&
+      (e = cudaMemsetAsync(ws.R + (size_t)ldx * P, 0, (size_t)ldx * (P_pad - P) * 8, s)) != cudaSuccess)
+    return e;
+  lasso_setup_kernel<<<P, 256, 0, s>>>(A);
+  if ((e = launch_gemm_tn_f64(D.Xs, ldx, ws.R, ldx, ws.XM, p_pad, D.p, P, ldx, s)) != cudaSuccess) return e;
+  if ((e = launch_gemm_tn_f64(D.Xs2, ldx, ws.R, ldx, ws.XI, p_pad, D.p, P, ldx, s)) != cudaSuccess) return e;
+  lasso_moments_kernel<<<dim3((p_pad + 255) / 256, P), 256, 0, s>>>(A);
+  lasso_resid0_kernel<<<P, 256, 0, s>>>(A);
+  if ((e = launch_gemm_tn_f64(D.Xs, ldx, ws.R, ldx, ws.G, p_pad, D.p, P, ldx, s)) != cudaSuccess) return e;
+  *launches += 6;
+  *gemm_cols += 3LL * P;
+  if (prm.auto_lambda) {
+    lasso_lambda_kernel<<<B, 256, 0, s>>>(A);
+    *launches += 1;
+  } else {
+    if ((e = cudaMemcpyAsync(ws.lam, lam_user, (size_t)kNLam * B * 8, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(ws.nlam_g, nlam_user, (size_t)B * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(ws.Lfinal, nlam_user, (size_t)B * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+  // ---- rounds ----
+  const size_t smem_staged = kFixedSmem + (size_t)2 * ldx * 8;
+  const bool staged = smem_staged <= 227 * 1024;
+  const size_t smem = staged ? smem_staged : kFixedSmem;
+  const int T = ldx <= 512 ? 128 : ldx <= 2560 ? 256 : ldx <= 6144 ? 512 : 1024;
+  int cur = 0;
+  if ((e = cudaMemcpyAsync(ws.h_counter, ws.counters, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  int live = ws.h_counter[0];
+  int rounds = 0;
+  while (live > 0) {
+    if (++rounds > 100000) return cudaErrorUnknown;
+    int* list = cur ? ws.list1 : ws.list0;
+    int* next = cur ? ws.list0 : ws.list1;
+    int* cnt = ws.counters + (cur ? 0 : 1);
+    if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
+    switch (T) {
+      case 128: e = launch_round_t<128>(A, list, next, cnt, live, staged, smem, s); break;
+      case 256: e = launch_round_t<256>(A, list, next, cnt, live, staged, smem, s); break;
+      case 512: e = launch_round_t<512>(A, list, next, cnt, live, staged, smem, s); break;
+      default: e = launch_round_t<1024>(A, list, next, cnt, live, staged, smem, s); break;
+    }
+    if (e != cudaSuccess) return e;
+    *launches += 1;
+    if ((e = cudaMemcpyAsync(ws.h_counter, cnt, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    live = ws.h_counter[0];
+    cur ^= 1;
+    if (live > 0) {
+      if ((e = launch_gemm_tn_f64(D.Xs, ldx, ws.R, ldx, ws.G, p_pad, D.p, live, ldx, s)) != cudaSuccess) return e;
+      *launches += 1;
+      *gemm_cols += live;
+    }
+  }
+  FinalArgs F;
+  F.R = A; F.lmin_user = lmin_user; F.MU = MU; F.out4 = out4; F.status = status; F.stats = stats;
+  F.cvout = cvout;
+  lasso_finalize_kernel<<<B, 256, 0, s>>>(F);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace saver

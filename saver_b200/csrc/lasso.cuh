@@ -1,0 +1,74 @@
+// lasso.cuh -- data structures of the batched Poisson-lasso path solver (lasso.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace saver {
+
+constexpr int kNX = 640;     // capacity of the ever-active list (glmnet pmax = min(2*dfmax+20, nvars))
+constexpr int kNLam = 128;   // capacity of a lambda sequence (glmnet nlambda = 100)
+constexpr int kMaxFolds = 16;
+
+enum ProbState : int { ST_INIT = 0, ST_SOLVE = 1, ST_WAIT_KKT = 2, ST_DONE = 3 };
+
+// One (gene, fit) problem: fit 0 = master fit on all pred cells, fit f > 0 = CV fold f held out.
+struct LassoProb {
+  int gene, fit;
+  int state;
+  int lidx;     // lambda index being solved
+  int lmu;      // number of committed solutions
+  int nin;      // ever-active count
+  int nS;       // strong-set size (length of the problem's Sidx list)
+  int jerr;     // glmnet code: 0 ok, -ilm maxit, -10000-ilm pmax overflow, >0 fatal
+  int nlp;      // coordinate-descent sweeps so far
+  int ngrad;    // full-gradient (X^T r over all p) rounds so far
+  int mtrain;   // training rows
+  int slot;     // column of R / G this problem used in the last round
+  double al, al0;   // current / previous lambda
+  double az;        // intercept
+  double qv;        // observation weight 1 / mtrain
+  double yb, dv0, dvr, shr;
+  double v0;        // sum of working weights
+  double sumr;      // sum of working residuals in R (standardisation shift of X^T r)
+  double cur_dev;   // deviance ratio of the current iterate
+  double cur_cv;    // held-out Poisson deviance (sum) of the current iterate
+  double ncv;       // held-out rows
+};
+
+struct LassoParams {
+  int B;            // genes in this block
+  int NF;           // fits per gene: 1 (path variant) or nfolds + 1 (CV variant)
+  int nfolds;
+  int auto_lambda;  // 1: glmnet's automatic sequence (master) + folds on the master grid; 0: user
+  int dfmax;        // glmnet dfmax (ne)
+  int nlam;         // nlambda for the automatic sequence
+  double thr;       // glmnet thresh
+  int maxit;        // glmnet maxit
+  double alf_wide;  // lambda ratio for flmin = 0.01 (nobs < nvars), computed on the host
+  double alf_tall;  // lambda ratio for flmin = 1e-4
+};
+
+// Device workspace of one block of problems (owned by the handle, grown on demand).
+struct LassoWs {
+  size_t cap_bytes = 0;
+  unsigned char* base = nullptr;
+  int *h_counter = nullptr;  // pinned host mirror of the active-problem counter
+  // carved pointers (valid for the current block)
+  double *R, *W, *WR;        // ldx x P_pad panels: GEMM operand, working weights, working residual
+  double *G, *XM, *XI;       // p_pad x P_pad tables: gradient, per-fit mean and 1/sd of Xs columns
+  int *MM, *SIDX;            // p_pad x P: 0 none, -1 strong only, >0 active position / strong list
+  int *IA;                   // kNX x P ever-active variables in order of entry
+  double *AACT;              // kNX x P coefficients in active-list order (standardised scale)
+  LassoProb* prob;           // P
+  double *lam;               // kNLam x B
+  int *nlam_g, *Lfinal, *gstat;   // B
+  double *gmean;             // B: mean of y over the pred cells
+  double *a0p, *devp;        // kNLam x B master path
+  int *ninp;                 // kNLam x B
+  double *cap;               // kNX x kNLam x B master coefficients per lambda
+  double *cvdev;             // kNLam x kMaxFolds x B held-out mean deviance
+  int *list0, *list1;        // P each: active problem lists (ping-pong)
+  int *counters;             // [2]
+  void release();
+};
+
+}  // namespace saver

@@ -19,8 +19,10 @@ struct saver_cuda_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  long long gemm_cols = 0;  // problem columns pushed through the gradient GEMM (lasso rounds)
   char err[512] = {0};
   DesignState design;
+  LassoWs lasso;
 };
 
 namespace {
@@ -136,6 +138,7 @@ int saver_cuda_destroy(saver_cuda_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->design.release();
+  h->lasso.release();
   cudaStreamDestroy(h->stream);
   delete h;
   return SAVER_OK;
@@ -319,5 +322,147 @@ int saver_cuda_maxcor(saver_cuda_handle h, const double* Y, int B, const int* se
   if (!dev) CU(cudaStreamSynchronize(s));
   return SAVER_OK;
 }
+
+// ---- expr.predict ----
+namespace {
+
+__global__ void pred_mask_kernel(const int* mask, int n, int B, int* fold) {
+  const size_t tot = (size_t)n * B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot;
+       i += (size_t)gridDim.x * blockDim.x)
+    fold[i] = mask ? (mask[i % n] != 0) : 1;
+}
+
+// glmnet's lambda ratio: alf = max(eps, flmin)^(1/(nlam-1)) with a REAL*4 exponent (Fortran
+// fishnet1); evaluated on the host so it matches libm's pow bit for bit.
+double lambda_ratio(double flmin, int nlam) {
+  const double eqs = flmin > 1e-6 ? flmin : 1e-6;
+  return nlam > 1 ? pow(eqs, (double)(1.0f / (float)(nlam - 1))) : 1.0;
+}
+
+}  // namespace
+
+int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int* self_col,
+                          const int* foldid, int nfolds, int dfmax, int nlambda, double thresh,
+                          double* mu, double* fit4, int* status, int* stats, double* cvout,
+                          int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!h->design.Xs) return fail(h, SAVER_ERR_STATE, "predict_cv: call saver_cuda_set_design first");
+  if (!Y || !foldid || !mu || !fit4 || !status || B < 0 || nfolds < 3 || nfolds > kMaxFolds ||
+      nlambda < 1 || nlambda > kNLam || dfmax < 1 || !(thresh > 0))
+    return fail(h, SAVER_ERR_ARG, "predict_cv: bad arguments");
+  if (B == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  const DesignState& D = h->design;
+  const size_t n = D.n;
+  InArr<double> dY;
+  InArr<int> dSelf, dFold;
+  OutArr<double> oMu, oFit, oCv;
+  OutArr<int> oSt, oStats;
+  CU(dY.bind(Y, n * B, dev, s));
+  CU(dSelf.bind(self_col, B, dev, s));
+  CU(dFold.bind(foldid, n * B, dev, s));
+  CU(oMu.bind(mu, n * B, dev, s));
+  CU(oFit.bind(fit4, (size_t)4 * B, dev, s));
+  CU(oSt.bind(status, B, dev, s));
+  CU(oStats.bind(stats, (size_t)4 * B, dev, s));
+  CU(oCv.bind(cvout, (size_t)3 * kNLam * B, dev, s));
+  LassoParams prm;
+  prm.NF = nfolds + 1; prm.nfolds = nfolds; prm.auto_lambda = 1; prm.dfmax = dfmax;
+  prm.nlam = nlambda; prm.thr = thresh; prm.maxit = 100000;
+  prm.alf_wide = lambda_ratio(0.01, nlambda);
+  prm.alf_tall = lambda_ratio(1e-4, nlambda);
+  const int chunk = lasso_max_block(prm.NF);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    prm.B = B - b0 < chunk ? B - b0 : chunk;
+    CU(lasso_run(D, h->lasso, prm, dY.d + n * b0, dFold.d + n * b0, dSelf.d ? dSelf.d + b0 : nullptr,
+                 nullptr, nullptr, nullptr, oMu.d + n * b0, oFit.d + (size_t)4 * b0, oSt.d + b0,
+                 oStats.d ? oStats.d + (size_t)4 * b0 : nullptr,
+                 oCv.d ? oCv.d + (size_t)3 * kNLam * b0 : nullptr, s, &h->launches, &h->gemm_cols));
+  }
+  CU(oMu.fetch(s)); CU(oFit.fetch(s)); CU(oSt.fetch(s)); CU(oStats.fetch(s)); CU(oCv.fetch(s));
+  if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}
+
+int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const int* self_col,
+                            const int* pred_mask, const double* lambda_max,
+                            const double* lambda_min, int dfmax, double thresh, double* mu,
+                            int* status, int* stats, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!h->design.Xs) return fail(h, SAVER_ERR_STATE, "predict_path: call saver_cuda_set_design first");
+  if (!Y || !mu || !status || !lambda_max || !lambda_min || B < 0 || dfmax < 1 || !(thresh > 0))
+    return fail(h, SAVER_ERR_ARG, "predict_path: bad arguments");
+  if (B == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  const DesignState& D = h->design;
+  const size_t n = D.n;
+  // lambda.seq = c(exp(seq(log(lmax), log(lmin), by = -0.2)), lmin), sorted decreasing as glmnet
+  // does with a user sequence (R/expr_predict.R:62-63); built on the host (always host arrays).
+  std::vector<double> lam((size_t)kNLam * B, 0.0);
+  std::vector<int> nlam(B, 0);
+  for (int g = 0; g < B; ++g) {
+    const double lmax = lambda_max[g], lmin = lambda_min[g];
+    double* lg = lam.data() + (size_t)kNLam * g;
+    int nl = 0;
+    if (lmax > 0 && lmin > 0 && lmax == lmax && lmin == lmin) {
+      const double from = log(lmax), to = log(lmin);
+      int nstep = (int)floor((to - from) / -0.2 + 1e-10);
+      if (nstep < 0) nstep = 0;
+      if (nstep + 2 > kNLam) return fail(h, SAVER_ERR_ARG, "predict_path: lambda sequence too long");
+      for (int i = 0; i <= nstep; ++i) lg[nl++] = exp(from + i * -0.2);
+      lg[nl++] = lmin;
+      for (int i = 1; i < nl; ++i) {  // insertion sort, decreasing
+        const double v = lg[i];
+        int j = i - 1;
+        while (j >= 0 && lg[j] < v) { lg[j + 1] = lg[j]; --j; }
+        lg[j + 1] = v;
+      }
+    } else {
+      lg[nl++] = lmax;  // degenerate input: single value, the solver reports the failure
+    }
+    nlam[g] = nl;
+  }
+  InArr<double> dY, dLam, dLmin;
+  InArr<int> dSelf, dMask, dNlam;
+  OutArr<double> oMu;
+  OutArr<int> oSt, oStats;
+  CU(dY.bind(Y, n * B, dev, s));
+  CU(dSelf.bind(self_col, B, dev, s));
+  CU(dMask.bind(pred_mask, n, dev, s));
+  CU(dLam.bind(lam.data(), lam.size(), false, s));
+  CU(dNlam.bind(nlam.data(), B, false, s));
+  CU(dLmin.bind(lambda_min, B, false, s));
+  CU(oMu.bind(mu, n * B, dev, s));
+  CU(oSt.bind(status, B, dev, s));
+  CU(oStats.bind(stats, (size_t)4 * B, dev, s));
+  LassoParams prm;
+  prm.NF = 1; prm.nfolds = 0; prm.auto_lambda = 0; prm.dfmax = dfmax; prm.nlam = 0;
+  prm.thr = thresh; prm.maxit = 100000; prm.alf_wide = prm.alf_tall = 1.0;
+  const int chunk = lasso_max_block(prm.NF);
+  DevBuf<int> fold;
+  DevBuf<double> fit4;
+  CU(fold.alloc(n * (size_t)(B < chunk ? B : chunk), s));
+  CU(fit4.alloc((size_t)4 * B, s));
+  pred_mask_kernel<<<592, 256, 0, s>>>(dMask.d, (int)n, B < chunk ? B : chunk, fold.p);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    prm.B = B - b0 < chunk ? B - b0 : chunk;
+    CU(lasso_run(D, h->lasso, prm, dY.d + n * b0, fold.p, dSelf.d ? dSelf.d + b0 : nullptr,
+                 dLam.d + (size_t)kNLam * b0, dNlam.d + b0, dLmin.d + b0, oMu.d + n * b0,
+                 fit4.p + (size_t)4 * b0, oSt.d + b0, oStats.d ? oStats.d + (size_t)4 * b0 : nullptr,
+                 nullptr, s, &h->launches, &h->gemm_cols));
+  }
+  CU(oMu.fetch(s)); CU(oSt.fetch(s)); CU(oStats.fetch(s));
+  CU(cudaStreamSynchronize(s));  // host staging vectors die with this frame
+  return SAVER_OK;
+}
+
+long long saver_cuda_gemm_columns(saver_cuda_handle h) { return h ? h->gemm_cols : 0; }
 
 }  // extern "C"

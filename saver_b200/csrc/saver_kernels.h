@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "lasso.cuh"
+
 namespace saver {
 
 constexpr int kPostInfo = 8;  // per-gene info record of calc_post (doubles)
@@ -54,6 +56,14 @@ cudaError_t launch_gemm_tn_f64(const double* A, int lda, const double* B, int ld
 cudaError_t launch_center_scale(const double* Y, int n, int ldr, int B, double* R, cudaStream_t s);
 cudaError_t launch_colmax(const double* C, int ldc, int p, int B, const int* self, double* out,
                           cudaStream_t s);
+
+// Batched Poisson-lasso paths of one block of genes (lasso.cu).  Device pointers throughout.
+int lasso_max_block(int NF);
+cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm, const double* Yn,
+                      const int* fold, const int* self, const double* lam_user,
+                      const int* nlam_user, const double* lmin_user, double* MU, double* out4,
+                      int* status, int* stats, double* cvout, cudaStream_t s, long long* launches,
+                      long long* gemm_cols);
 
 size_t calc_post_smem_bytes(int n, int* stage);
 cudaError_t launch_calc_post(const CalcPostArgs& A, cudaStream_t stream);

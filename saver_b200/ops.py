@@ -120,3 +120,80 @@ def maxcor(Y, self_col=None, handle=None):
         raise ValueError("Y has %d cells, design has %d" % (n, h.design_shape[0]))
     h.check(h.lib.saver_cuda_maxcor(h.h, ptr(Y), B, ptr(sc), ptr(out), int(dev)))
     return out
+
+
+NLAM_CAP = 128
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def predict_cv(Y, foldid, self_col=None, nfolds=5, dfmax=300, nlambda=100, thresh=1e-7,
+               want_stats=False, want_cv=False, handle=None):
+    """expr.predict, CV variant (R/expr_predict.R:39-60) for a panel.
+
+    Y (B, n) normalised expression; foldid (B, n) ints: 0 = not a pred cell, 1..nfolds.
+    Returns dict(mu (B, n), lambda_max, lambda_min, sd_cv, idx, status[, stats, cv]).
+    """
+    h = handle or default_handle()
+    dev = is_device(Y)
+    if dev:
+        import torch
+        B, n = Y.shape
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=Y.device)  # noqa: E731
+        f64, i32 = torch.float64, torch.int32
+        sc = self_col
+        assert foldid.dtype == torch.int32 and foldid.is_contiguous() and Y.is_contiguous()
+    else:
+        Y = _f64(np.atleast_2d(Y))
+        B, n = Y.shape
+        foldid = _i32(foldid).reshape(B, n)
+        sc = None if self_col is None else _i32(self_col)
+        mk = lambda shape, dt: np.empty(shape, dtype=dt)  # noqa: E731
+        f64, i32 = np.float64, np.int32
+    if n != h.design_shape[0]:
+        raise ValueError("Y has %d cells, design has %d" % (n, h.design_shape[0]))
+    mu = mk((B, n), f64)
+    fit4 = mk((B, 4), f64)
+    status = mk((B,), i32)
+    stats = mk((B, 4), i32) if want_stats else None
+    cv = mk((B, 3, NLAM_CAP), f64) if want_cv else None
+    h.check(h.lib.saver_cuda_predict_cv(h.h, ptr(Y), B, ptr(sc), ptr(foldid), int(nfolds), int(dfmax),
+                                        int(nlambda), _D(float(thresh)), ptr(mu), ptr(fit4),
+                                        ptr(status), ptr(stats), ptr(cv), int(dev)))
+    return dict(mu=mu, lambda_max=fit4[:, 0], lambda_min=fit4[:, 1], sd_cv=fit4[:, 2],
+                idx=fit4[:, 3], status=status, stats=stats, cv=cv)
+
+
+def predict_path(Y, lambda_max, lambda_min, self_col=None, pred_mask=None, dfmax=300,
+                 thresh=1e-7, want_stats=False, handle=None):
+    """expr.predict, fixed-lambda variant (R/expr_predict.R:61-82) for a panel."""
+    h = handle or default_handle()
+    dev = is_device(Y)
+    lmax = _f64(np.asarray(lambda_max, dtype=np.float64))
+    lmin = _f64(np.asarray(lambda_min, dtype=np.float64))
+    if dev:
+        import torch
+        B, n = Y.shape
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=Y.device)  # noqa: E731
+        f64, i32 = torch.float64, torch.int32
+        sc, pm = self_col, pred_mask
+    else:
+        Y = _f64(np.atleast_2d(Y))
+        B, n = Y.shape
+        sc = None if self_col is None else _i32(self_col)
+        pm = None if pred_mask is None else _i32(pred_mask)
+        mk = lambda shape, dt: np.empty(shape, dtype=dt)  # noqa: E731
+        f64, i32 = np.float64, np.int32
+    if n != h.design_shape[0]:
+        raise ValueError("Y has %d cells, design has %d" % (n, h.design_shape[0]))
+    if lmax.size != B or lmin.size != B:
+        raise ValueError("lambda_max / lambda_min need one value per gene")
+    mu = mk((B, n), f64)
+    status = mk((B,), i32)
+    stats = mk((B, 4), i32) if want_stats else None
+    h.check(h.lib.saver_cuda_predict_path(h.h, ptr(Y), B, ptr(sc), ptr(pm), ptr(lmax), ptr(lmin),
+                                          int(dfmax), _D(float(thresh)), ptr(mu), ptr(status),
+                                          ptr(stats), int(dev)))
+    return dict(mu=mu, status=status, stats=stats)
