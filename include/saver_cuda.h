@@ -135,9 +135,35 @@ SAVER_API int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int 
                                       int dfmax, double thresh, double* mu, int* status,
                                       int* stats, int device_ptrs);
 
+/* ---- calc.estimate (R/calc_estimate.R:65-161): the data-parallel loop body for a block ----
+ * X: n x B raw counts of the block (one gene per column); sf: n normalised size factors.
+ * self_col[B]: column of x.est with the gene's own name or -1 (R/calc_estimate.R:103);
+ * is_pred[B]: the gene's name is in pred.gene.names (NULL = all);  pred_mask: n ints, non-zero =
+ * pred cell (NULL = all);  foldid: n x B per-gene CV folds 1..nfolds (mode 1 only; the R host
+ * draws them with set.seed(j); sample(rep(seq(nfolds), length = N)) exactly as cv.glmnet would).
+ * mode: 0 = null.model (means), 1 = coefs NULL (cross-validated lasso), 2 = coefs given
+ * (est.lambda + fixed-lambda path).  calc_maxcor / cutoff / coefs[2] as in the R signature.
+ * est, se (NULL when estimates.only): n x B.  info6: six vectors of B doubles back to back =
+ * maxcor, lambda.max, lambda.min, sd.cv, pred.time, var.time (seconds per gene, device time of
+ * the block / B).  mu_out (optional): n x B predictions.  status_out (optional): per gene
+ * 0 ok / 1 sd(y)==0 / 2 fit failed -> mean (the reference's tryCatch fallbacks). */
+SAVER_API int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, int n, int B,
+                                       const double* sf, double scale_sf, const int* self_col,
+                                       const int* is_pred, const int* pred_mask, const int* foldid,
+                                       int nfolds, int mode, int calc_maxcor, double cutoff,
+                                       const double* coefs, int dfmax, int nlambda, double thresh,
+                                       double* est, double* se, double* info6, double* mu_out,
+                                       int* status_out, int device_ptrs);
+
 /* Problem columns pushed through the gradient GEMM so far (roofline accounting in bench.py):
  * every column is one 2 * n * p flop contraction against the resident design. */
 SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);
+
+/* Cumulative accounting since the handle was created (CUDA-event device times, ms):
+ * [0] lasso round kernels, [1] gradient GEMMs of the rounds, [2] lasso block setup (moments,
+ * initial gradient), [3] variance/posterior kernel inside calc_estimate, [4] design columns the
+ * round kernels streamed (n x 8 bytes each), [5] GEMM problem columns, [6] rounds, [7] launches. */
+SAVER_API int saver_cuda_counters(saver_cuda_handle h, double* out8);
 
 #ifdef __cplusplus
 }

@@ -517,6 +517,12 @@ static void fishnet1(int m, int p, const double *xs, const int *ju, const double
     const double q = 1.0 / m;
     double yb = 0;
     for (int i = 0; i < m; ++i) { t[i] = q * y[i]; yb += t[i]; }
+    if (!(yb > 0.0)) { /* fishnet: "no positive observations" -> fatal jerr, R raises an error */
+        fi->jerr = 9999; fi->lmu = 0; fi->nlp = 0; fi->ngrad = 0; fi->nulldev = 0;
+        free(a); free(as); free(ga); free(v); free(mm); free(ixx);
+        free(t); free(w); free(wr); free(f);
+        return;
+    }
     double az = log(yb), dv0 = yb * (az - 1.0);
     for (int i = 0; i < m; ++i) { w[i] = q * yb; f[i] = az; wr[i] = t[i] - w[i]; }
     double v0 = yb, dvr = -yb;

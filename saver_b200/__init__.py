@@ -4,7 +4,8 @@ Host-side mirror of the reference's R function API over the C ABI of libsaver_cu
 (include/saver_cuda.h).  No CPU fallback: every numerical entry point runs hand-written
 sm_100a CUDA and raises if the library or a CUDA device is missing.
 """
-from . import ops  # noqa: F401
+from . import host, ops  # noqa: F401
+from .host import SaverError, SaverResult, saver, saver_fit  # noqa: F401
 from ._lib import Handle, SaverCudaError, default_handle  # noqa: F401
 
 __version__ = "0.1.0"

@@ -36,6 +36,7 @@ namespace saver {
 void LassoWs::release() {
   if (base) cudaFree(base);
   if (h_counter) cudaFreeHost(h_counter);
+  for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
   base = nullptr;
   h_counter = nullptr;
   cap_bytes = 0;
@@ -313,6 +314,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
 
   const int tid = threadIdx.x;
   int phase = 0;
+  unsigned ncols = 0;  // design columns this CTA streamed (roofline accounting)
   const int pid = list[blockIdx.x];
   LassoProb* PR = A.ws.prob + pid;
   const int g = PR->gene, fit = PR->fit, slot = PR->slot;
@@ -507,6 +509,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
           const double* c0 = Xs + (size_t)SIc[0] * ldx;
           for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(c0 + i);
         }
+        ncols += nS;
         for (int s = 0; s < nS; ++s) {
           const int k = SIc[s];
           const double* col = Xs + (size_t)k * ldx;
@@ -570,6 +573,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
         while (true) {  // sweeps over the ever-active list
           ++nlp;
           dlx = 0.0;
+          ncols += nin;
           for (int l = 0; l < nin; ++l) {
             const int k = ia[l];
             const double* col = Xs + (size_t)k * ldx;
@@ -620,6 +624,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
       }
       bsum<1>(c0p, red, phase);
       const double c0 = az - c0p[0];
+      ncols += nin;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum w, sum t f, sum wr, held-out deviance
       for (int i = 2 * tid; i < ldx; i += 2 * T) {
         double f0 = c0, f1 = c0;
@@ -702,6 +707,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
     if (tid == 0) PR->slot = pos;
   }
   if (tid == 0) {
+    atomicAdd(A.ws.colcount, (unsigned long long)ncols);
     if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
     PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
     PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
@@ -918,7 +924,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oDv = take((size_t)kNLam * B * 8), oNi = take((size_t)kNLam * B * 4),
                oCap = take((size_t)kNX * kNLam * B * 8),
                oCv = take((size_t)kNLam * kMaxFolds * B * 8), oL0 = take((size_t)P * 4),
-               oL1 = take((size_t)P * 4), oCt = take(64);
+               oL1 = take((size_t)P * 4), oCt = take(64), oCc = take(64);
   cudaError_t e;
   if (off > ws.cap_bytes) {
     if (ws.base) {
@@ -940,12 +946,17 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   ws.gmean = (double*)(b + oGm); ws.a0p = (double*)(b + oA0); ws.devp = (double*)(b + oDv);
   ws.ninp = (int*)(b + oNi); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
   ws.list0 = (int*)(b + oL0); ws.list1 = (int*)(b + oL1); ws.counters = (int*)(b + oCt);
+  ws.colcount = (unsigned long long*)(b + oCc);
+  for (auto& ev : ws.ev)
+    if (!ev && (e = cudaEventCreate(&ev)) != cudaSuccess) return e;
 
   RoundArgs A;
   A.Xs = D.Xs; A.xsd = D.xsd; A.n = n; A.ldx = ldx; A.p = D.p; A.p_pad = p_pad; A.P = P;
   A.prm = prm; A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
 
   if ((e = cudaMemsetAsync(ws.counters, 0, 64, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.colcount, 0, 64, s)) != cudaSuccess) return e;
+  cudaEventRecord(ws.ev[0], s);
   // the padding columns of the GEMM panel must hold finite numbers
   if (P_pad > P &&
       (e = cudaMemsetAsync(ws.R + (size_t)ldx * P, 0, (size_t)ldx * (P_pad - P) * 8, s)) != cudaSuccess)
@@ -974,8 +985,15 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   const size_t smem = staged ? smem_staged : kFixedSmem;
   const int T = ldx <= 512 ? 128 : ldx <= 2560 ? 256 : ldx <= 6144 ? 512 : 1024;
   int cur = 0;
+  cudaEventRecord(ws.ev[1], s);
   if ((e = cudaMemcpyAsync(ws.h_counter, ws.counters, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]);
+    ws.ms_setup += ms;
+  }
+  bool gemm_pending = false;
   int live = ws.h_counter[0];
   int rounds = 0;
   while (live > 0) {
@@ -984,6 +1002,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     int* next = cur ? ws.list0 : ws.list1;
     int* cnt = ws.counters + (cur ? 0 : 1);
     if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
+    cudaEventRecord(ws.ev[0], s);
     switch (T) {
       case 128: e = launch_round_t<128>(A, list, next, cnt, live, staged, smem, s); break;
       case 256: e = launch_round_t<256>(A, list, next, cnt, live, staged, smem, s); break;
@@ -992,15 +1011,36 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     }
     if (e != cudaSuccess) return e;
     *launches += 1;
+    cudaEventRecord(ws.ev[1], s);
     if ((e = cudaMemcpyAsync(ws.h_counter, cnt, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]);
+      ws.ms_round += ms;
+      if (gemm_pending) {
+        cudaEventElapsedTime(&ms, ws.ev[2], ws.ev[3]);
+        ws.ms_gemm += ms;
+      }
+      ws.rounds += 1;
+    }
     live = ws.h_counter[0];
     cur ^= 1;
+    gemm_pending = false;
     if (live > 0) {
+      cudaEventRecord(ws.ev[2], s);
       if ((e = launch_gemm_tn_f64(D.Xs, ldx, ws.R, ldx, ws.G, p_pad, D.p, live, ldx, s)) != cudaSuccess) return e;
+      cudaEventRecord(ws.ev[3], s);
+      gemm_pending = true;
       *launches += 1;
       *gemm_cols += live;
     }
+  }
+  {
+    unsigned long long cc = 0;
+    if ((e = cudaMemcpyAsync(&cc, ws.colcount, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    ws.cols_streamed += cc;
   }
   FinalArgs F;
   F.R = A; F.lmin_user = lmin_user; F.MU = MU; F.out4 = out4; F.status = status; F.stats = stats;

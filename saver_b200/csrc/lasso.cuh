@@ -68,6 +68,12 @@ struct LassoWs {
   double *cvdev;             // kNLam x kMaxFolds x B held-out mean deviance
   int *list0, *list1;        // P each: active problem lists (ping-pong)
   int *counters;             // [2]
+  unsigned long long* colcount;  // design columns streamed by the round kernels (cumulative)
+  // accounting (host side, cumulative over the handle's life)
+  double ms_round = 0, ms_gemm = 0, ms_setup = 0;
+  unsigned long long cols_streamed = 0;
+  long long rounds = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void release();
 };
 

@@ -11,91 +11,11 @@
 #include <new>
 #include <vector>
 
-#include "saver_kernels.h"
+#include "ctx.h"
 
 using namespace saver;
 
-struct saver_cuda_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  long long launches = 0;
-  long long gemm_cols = 0;  // problem columns pushed through the gradient GEMM (lasso rounds)
-  char err[512] = {0};
-  DesignState design;
-  LassoWs lasso;
-};
-
 namespace {
-
-int fail(saver_cuda_ctx* h, int code, const char* fmt, ...) {
-  if (h) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(h->err, sizeof h->err, fmt, ap);
-    va_end(ap);
-  }
-  return code;
-}
-
-#define CU(call)                                                                         \
-  do {                                                                                   \
-    cudaError_t e_ = (call);                                                             \
-    if (e_ != cudaSuccess)                                                               \
-      return fail(h, e_ == cudaErrorMemoryAllocation ? SAVER_ERR_NOMEM : SAVER_ERR_CUDA, \
-                  "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
-  } while (0)
-
-// Stream-ordered device buffer (cudaMallocAsync pool keeps freed blocks cached).
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  cudaStream_t s = nullptr;
-  cudaError_t alloc(size_t count, cudaStream_t stream) {
-    s = stream;
-    if (count == 0) count = 1;
-    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
-  }
-  ~DevBuf() {
-    if (p) cudaFreeAsync(p, s);
-  }
-};
-
-// Input array that is either already on the device or must be uploaded.
-template <typename T>
-struct InArr {
-  DevBuf<T> buf;
-  const T* d = nullptr;
-  cudaError_t bind(const T* src, size_t count, bool on_device, cudaStream_t s) {
-    if (!src) { d = nullptr; return cudaSuccess; }
-    if (on_device) { d = src; return cudaSuccess; }
-    cudaError_t e = buf.alloc(count, s);
-    if (e != cudaSuccess) return e;
-    d = buf.p;
-    return cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
-  }
-};
-
-// Output array: device-resident caller buffer, or a temp that is copied back.
-template <typename T>
-struct OutArr {
-  DevBuf<T> buf;
-  T* d = nullptr;
-  T* host = nullptr;
-  size_t count = 0;
-  cudaError_t bind(T* dst, size_t n, bool on_device, cudaStream_t s) {
-    count = n;
-    if (!dst) { d = nullptr; return cudaSuccess; }
-    if (on_device) { d = dst; return cudaSuccess; }
-    host = dst;
-    cudaError_t e = buf.alloc(n, s);
-    d = buf.p;
-    return e;
-  }
-  cudaError_t fetch(cudaStream_t s) {
-    if (!host || !d) return cudaSuccess;
-    return cudaMemcpyAsync(host, d, count * sizeof(T), cudaMemcpyDeviceToHost, s);
-  }
-};
 
 __global__ void fill_panel_kernel(double* dst, const double* scalars, int n, int B) {
   const size_t tot = (size_t)n * B;
@@ -464,5 +384,18 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
 }
 
 long long saver_cuda_gemm_columns(saver_cuda_handle h) { return h ? h->gemm_cols : 0; }
+
+int saver_cuda_counters(saver_cuda_handle h, double* out8) {
+  if (!h || !out8) return SAVER_ERR_ARG;
+  out8[0] = h->lasso.ms_round;
+  out8[1] = h->lasso.ms_gemm;
+  out8[2] = h->lasso.ms_setup;
+  out8[3] = h->ms_post;
+  out8[4] = (double)h->lasso.cols_streamed;
+  out8[5] = (double)h->gemm_cols;
+  out8[6] = (double)h->lasso.rounds;
+  out8[7] = (double)h->launches;
+  return SAVER_OK;
+}
 
 }  // extern "C"

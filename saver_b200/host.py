@@ -1,0 +1,515 @@
+"""Host-side mirror of the reference's R API for the expression-recovery path.
+
+R is not installable in the build image, so the host layer that the reference
+writes in R (R/saver.R, R/saver_fit.R, R/calc_estimate.R, R/utils.R) is mirrored here in Python
+with the same names, argument meaning and error behaviour; INTEGRATION.md shows the R wrappers and
+the ``.Call`` shim that bind the same C ABI.  All numerical work goes through libsaver_cuda
+(``saver_cuda_calc_estimate`` = one call per stage block); there is no CPU fallback.
+
+Mapping (reference file:line -> here):
+    saver                R/saver.R:98-179          saver()
+    saver.fit            R/saver_fit.R:56-463      saver_fit()
+    saver.fit.mean/.null R/saver_fit.R:467-628     saver_fit_mean(), saver_fit_null()
+    calc.estimate        R/calc_estimate.R:65-161  CudaBackend.calc_estimate()
+    clean.data etc.      R/utils.R                 clean_data(), calc_size_factor(), ...
+"""
+import time
+
+import numpy as np
+
+from . import ops
+
+
+class SaverError(ValueError):
+    """R's stop(): argument validation failures of the reference API."""
+
+
+# ----------------------------------------------------------------------------------------------
+# R/utils.R
+# ----------------------------------------------------------------------------------------------
+def clean_data(x):
+    """clean.data (R/utils.R:2-31): values < 0.001 -> 0, drop all-zero cells.
+
+    Returns (x, kept_cells).  x is genes x cells; scipy.sparse matrices are densified per block by
+    the caller, like ``as.matrix(x)`` in R/calc_estimate.R:69."""
+    sparse = hasattr(x, "tocsc")
+    if sparse:
+        x = x.tocsc(copy=True).astype(np.float64)
+        x.data[x.data < 0.001] = 0
+        x.eliminate_zeros()
+        if x.ndim != 2 or x.shape[1] <= 1:
+            raise SaverError("x should be a matrix with 2 or more columns")
+        cs = np.asarray(x.sum(0)).ravel()
+    else:
+        x = np.array(x, dtype=np.float64, copy=True)
+        if x.ndim != 2 or x.shape[1] <= 1:
+            raise SaverError("x should be a matrix with 2 or more columns")
+        x[x < 0.001] = 0
+        cs = x.sum(0)
+    keep = cs != 0
+    if not keep.all():
+        x = x[:, np.where(keep)[0]]
+    return x, keep
+
+
+def check_mu(x, mu):
+    """check.mu (R/utils.R:33-51)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    if mu.shape != tuple(x.shape):
+        raise SaverError("x and mu must have same dimensions")
+    cs = np.asarray(x.sum(0)).ravel()
+    if cs.min() == 0:
+        mu = mu[:, cs != 0]
+    return mu
+
+
+def calc_size_factor(x, size_factor, ncells):
+    """calc.size.factor (R/utils.R:70-86) -> (sf, scale_sf)."""
+    if size_factor is None:
+        cs = np.asarray(x.sum(0)).ravel().astype(np.float64)
+        return cs / cs.mean(), 1.0
+    sfv = np.atleast_1d(np.asarray(size_factor, dtype=np.float64))
+    if sfv.size == ncells:
+        if sfv.min() <= 0:
+            raise SaverError("Size factor must be greater than 0")
+        return sfv / sfv.mean(), float(sfv.mean())
+    if sfv.size == 1 and sfv[0] == 1:
+        return np.ones(ncells), 1.0
+    if sfv.min() <= 0:
+        raise SaverError("Size factor must be greater than 0")
+    raise SaverError("Not a valid size factor")
+
+
+def get_pred_cells(pred_cells, ncells):
+    """get.pred.cells (R/utils.R:88-98); 0-based indices here."""
+    if pred_cells is None:
+        return np.arange(ncells)
+    pc = np.asarray(pred_cells, dtype=np.int64)
+    if pc.min() < 0 or pc.max() >= ncells:
+        raise SaverError("pred.cells must be column indices of x")
+    return pc
+
+
+def get_pred_genes(x, pred_genes, npred, ngenes):
+    """get.pred.genes (R/utils.R:100-115); 0-based indices here."""
+    rs = np.asarray(x.sum(1)).ravel()
+    if pred_genes is not None:
+        pg = np.asarray(pred_genes, dtype=np.int64)
+        if pg.min() < 0 or pg.max() >= ngenes:
+            raise SaverError("pred.genes must be row indices of x")
+        return pg
+    if npred is None:
+        return np.where(rs != 0)[0]
+    if npred < ngenes:
+        npred = min(int((rs != 0).sum()), int(npred))
+        return np.argsort(-rs / x.shape[1], kind="stable")[:npred]
+    raise SaverError("npred must be less than number of rows in x")
+
+
+def get_chunk(length, n):
+    """get.chunk (R/utils.R:118-126)."""
+    cs = np.stack([np.arange(100, 151), np.arange(99, 48, -1)], 1).ravel()
+    r = np.zeros(cs.size)
+    for i, c in enumerate(cs):
+        r[i] = int(np.ceil(length / c)) % n
+        if r[i] == 0:
+            return int(c)
+    return int(cs[int(np.argmax(r))])
+
+
+def est_lambda(y, r, coefs):
+    """est.lambda (R/utils.R:129-134)."""
+    y = np.asarray(y, dtype=np.float64)
+    n = y.size
+    lmax = r * y.std(ddof=1) * np.sqrt((n - 1) / n)
+    lmin = lmax * np.exp(-np.sqrt(max(0.0, coefs[0] + coefs[1] * r)))
+    return np.array([lmax, lmin])
+
+
+def _lm(y, x):
+    """lm(y ~ x)$coefficients with NA / non-finite rows dropped (na.omit)."""
+    ok = np.isfinite(x) & np.isfinite(y)
+    A = np.stack([np.ones(ok.sum()), x[ok]], 1)
+    return np.linalg.lstsq(A, y[ok], rcond=None)[0]
+
+
+# ----------------------------------------------------------------------------------------------
+# fold assignment = what cv.glmnet draws after set.seed(j) (R/expr_predict.R:35-43)
+# ----------------------------------------------------------------------------------------------
+def draw_folds(seeds, N, nfolds=5, fold_seed=0, method="philox"):
+    """foldid for each gene: a permutation of rep(1..nfolds, length = N).
+
+    seeds: the per-gene ``j`` of R/calc_estimate.R:98 (1-based position inside the stage block).
+    method "philox": counter-based stream keyed on (fold_seed, j) -- reproducible and independent
+    of how genes are split over blocks or GPUs.  method "R": base R's set.seed(j); sample(...)
+    (Mersenne-Twister + rejection sampling, saver_b200.rrng)."""
+    seeds = np.asarray(seeds, dtype=np.int64)
+    base = (np.arange(N) % nfolds + 1).astype(np.int32)
+    out = np.empty((seeds.size, N), dtype=np.int32)
+    if method == "R":
+        from . import rrng
+        for i, j in enumerate(seeds):
+            out[i] = base[rrng.sample_perm(int(j), N)]
+        return out
+    for i, j in enumerate(seeds):
+        rng = np.random.Generator(np.random.Philox(key=[int(fold_seed) & (2**63 - 1), int(j)]))
+        out[i] = base[np.argsort(rng.random(N), kind="stable")]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# calc.estimate on the device
+# ----------------------------------------------------------------------------------------------
+class CudaBackend:
+    """Runs calc.estimate blocks through libsaver_cuda on one device.
+
+    ``rank`` / ``world``: genes of every stage are dealt round-robin over the ranks of a
+    torch.distributed job (one process per GPU); results are gathered on every rank because the
+    stage schedule needs maxcor / sd.cv / lambda of the finished stage (R/saver_fit.R:158,244)."""
+
+    def __init__(self, handle=None, comm=None, block=4096):
+        from ._lib import default_handle
+        self.handle = handle or default_handle()
+        self.comm = comm
+        self.block = int(block)
+
+    def set_design(self, xest):
+        ops.set_design(xest, handle=self.handle)
+
+    def calc_estimate(self, x, sf, scale_sf, mode, cutoff=0.0, coefs=None, self_col=None,
+                      is_pred=None, pred_mask=None, foldid=None, nfolds=5, calc_maxcor=False,
+                      estimates_only=False, want_mu=False, dfmax=300, nlambda=100, thresh=1e-7):
+        """One block: x (B, n) raw counts.  Returns the 8-tuple of R/calc_estimate.R:159-160 as a
+        dict (est, se, maxcor, lambda_max, lambda_min, sd_cv, ct, vt) plus status (and mu)."""
+        return ops.calc_estimate(x, sf, scale_sf, mode, cutoff=cutoff, coefs=coefs,
+                                 self_col=self_col, is_pred=is_pred, pred_mask=pred_mask,
+                                 foldid=foldid, nfolds=nfolds, calc_maxcor=calc_maxcor,
+                                 want_se=not estimates_only, want_mu=want_mu, dfmax=dfmax,
+                                 nlambda=nlambda, thresh=thresh, handle=self.handle)
+
+
+class SaverResult:
+    """The ``saver`` S3 object (R/saver.R:173-175; fields R/saver_fit.R:66-70)."""
+
+    def __init__(self, estimate, se, info, mu=None, gene_names=None, cell_names=None):
+        self.estimate = estimate
+        self.se = se
+        self.info = info
+        self.mu = mu
+        self.gene_names = gene_names
+        self.cell_names = cell_names
+
+
+def _dense_rows(x, rows):
+    if hasattr(x, "tocsc"):
+        return np.asarray(x.tocsr()[rows].todense(), dtype=np.float64)
+    return np.ascontiguousarray(x[rows], dtype=np.float64)
+
+
+class _Fit:
+    """State shared by the stages of saver.fit (est / se / info assembly, R/saver_fit.R:60-70)."""
+
+    def __init__(self, x, sf, scale_sf, ngenes, ncells, estimates_only, backend, keep_mu, comm):
+        self.x, self.sf, self.scale_sf = x, sf, scale_sf
+        self.backend, self.comm = backend, comm
+        self.estimates_only = estimates_only
+        self.est = np.zeros((ngenes, ncells))
+        self.se = None if estimates_only else np.zeros((ngenes, ncells))
+        self.mu = np.zeros((ngenes, ncells)) if keep_mu else None
+        z = lambda: np.zeros(ngenes)  # noqa: E731
+        self.info = {"size.factor": scale_sf * sf, "maxcor": z(), "lambda.max": z(),
+                     "lambda.min": z(), "sd.cv": z(), "pred.time": z(), "var.time": z(),
+                     "cutoff": 0.0, "lambda.coefs": 0.0, "total.time": 0.0}
+        self.status = np.zeros(ngenes, dtype=np.int32)
+        self.owner = np.zeros(ngenes, dtype=np.int32)
+        self.seed_of = np.zeros(ngenes, dtype=np.int64)   # set.seed(j) of each cross-validated gene
+
+    def gather(self):
+        """Every rank receives the rows the other ranks computed (a no-op on one process)."""
+        if self.comm and self.comm.world > 1:
+            self.est = self.comm.gather_rows(self.est, self.owner)
+            if self.se is not None:
+                self.se = self.comm.gather_rows(self.se, self.owner)
+            if self.mu is not None:
+                self.mu = self.comm.gather_rows(self.mu, self.owner)
+
+    def run(self, ind, mode, cutoff, coefs, calc_maxcor, self_col_of, is_pred_of, pred_mask,
+            npred_cells, nfolds, fold_seed, fold_method):
+        """calc.estimate(x[ind, ], ...) for one stage; genes are dealt over the ranks."""
+        ind = np.asarray(ind, dtype=np.int64)
+        if ind.size == 0:
+            return
+        rank, world = (self.comm.rank, self.comm.world) if self.comm else (0, 1)
+        pos = np.arange(ind.size)
+        mine = pos[rank::world]
+        self.owner[ind] = pos % world
+        keys = ("maxcor", "lambda.max", "lambda.min", "sd.cv", "pred.time", "var.time")
+        loc = {k: np.zeros(mine.size) for k in keys}
+        loc_status = np.zeros(mine.size, dtype=np.int32)
+        blk = self.backend.block
+        for b0 in range(0, mine.size, blk):
+            p = mine[b0:b0 + blk]
+            g = ind[p]
+            xb = _dense_rows(self.x, g)
+            fold = None
+            if mode == 1:
+                # seed j = 1-based position of the gene inside the stage block (R/calc_estimate.R:98)
+                fold = np.zeros((g.size, xb.shape[1]), dtype=np.int32)
+                pc = np.where(pred_mask)[0] if pred_mask is not None else np.arange(xb.shape[1])
+                fold[:, pc] = draw_folds(p + 1, npred_cells, nfolds, fold_seed, fold_method)
+                self.seed_of[g] = p + 1
+            r = self.backend.calc_estimate(
+                xb, self.sf, self.scale_sf, mode, cutoff=cutoff, coefs=coefs,
+                self_col=self_col_of[g], is_pred=is_pred_of[g], pred_mask=pred_mask, foldid=fold,
+                nfolds=nfolds, calc_maxcor=calc_maxcor, estimates_only=self.estimates_only,
+                want_mu=self.mu is not None)
+            self.est[g] = r["est"]
+            if self.se is not None:
+                self.se[g] = r["se"]
+            if self.mu is not None:
+                self.mu[g] = r["mu"]
+            sl = slice(b0, b0 + p.size)
+            loc["maxcor"][sl] = r["maxcor"]
+            loc["lambda.max"][sl] = r["lambda_max"]
+            loc["lambda.min"][sl] = r["lambda_min"]
+            loc["sd.cv"][sl] = r["sd_cv"]
+            loc["pred.time"][sl] = r["ct"]
+            loc["var.time"][sl] = r["vt"]
+            loc_status[sl] = r["status"]
+        if self.comm and world > 1:
+            # per-gene scalars of the stage are needed by every rank (lm fits of the schedule)
+            packed = np.stack([loc[k] for k in keys] + [loc_status.astype(np.float64)], 0)
+            parts = self.comm.allgather_ragged(packed)
+            for r_, part in enumerate(parts):
+                g = ind[pos[r_::world]]
+                for i, k in enumerate(keys):
+                    self.info[k][g] = part[i]
+                self.status[g] = part[len(keys)].astype(np.int32)
+        else:
+            g = ind[mine]
+            for k in keys:
+                self.info[k][g] = loc[k]
+            self.status[g] = loc_status
+
+
+def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, null_model,
+              ngenes=None, ncells=None, gene_names=None, cell_names=None, estimates_only=False,
+              *, self_col=None, backend=None, comm=None, perm="identity", fold_seed=0,
+              fold_method="philox", nfolds=5, keep_mu=False, messages=None, gather=True):
+    """saver.fit (R/saver_fit.R:56-463): the stage schedule.
+
+    x (genes x cells counts), x_est ((p, n) = t(x.est) of R/saver.R:157, gene-major),
+    pred_genes / pred_cells 0-based.  self_col[g]: the x_est column carrying gene g's own name or
+    -1 (R/calc_estimate.R:103 compares names; indices here).
+    perm: "identity" or an int seed -- the reference permutes genes with the ambient RNG
+    (R/saver_fit.R:87-92); the permutation only decides which genes get cross-validated in
+    do.fast and the per-gene seeds."""
+    msg = messages or (lambda *a: None)
+    ngenes = x.shape[0] if ngenes is None else ngenes
+    ncells = x.shape[1] if ncells is None else ncells
+    backend = backend or CudaBackend(comm=comm)
+    nworkers = max(int(ncores), 1)
+    fit = _Fit(x, sf, scale_sf, ngenes, ncells, estimates_only, backend, keep_mu, comm)
+    info = fit.info
+    msg("Running SAVER with %d worker(s)" % nworkers)
+    pred_genes = np.asarray(pred_genes, dtype=np.int64)
+    rs = np.asarray(x[pred_genes].sum(1)).ravel() if pred_genes.size else np.zeros(0)
+    pred1 = pred_genes[rs > 0]
+    npred = pred_genes.size
+    if not null_model:
+        msg("Calculating predictions for %d genes using %d genes and %d cells..."
+            % (npred, x_est.shape[0], x_est.shape[1]))
+        if comm is not None and comm.world > 1 and comm.backend == "nccl":
+            # the design is uploaded once by rank 0 and broadcast over NVLink (NCCL)
+            backend.set_design(comm.broadcast_array(x_est if comm.rank == 0 else None,
+                                                    keep_on_device=True))
+        else:
+            backend.set_design(x_est)
+    else:
+        msg("Using means as predictions.")
+    st = time.time()
+    rest = np.setdiff1d(np.arange(ngenes), pred1, assume_unique=False)
+    if perm == "identity":
+        ind = np.concatenate([pred1, rest])
+    else:
+        rng = np.random.default_rng(perm)
+        ind = np.concatenate([rng.permutation(pred1), rng.permutation(rest)])
+    self_col_of = np.full(ngenes, -1, dtype=np.int32)
+    if self_col is not None:
+        self_col_of[:] = np.asarray(self_col, dtype=np.int32)
+    is_pred_of = np.zeros(ngenes, dtype=np.int32)
+    is_pred_of[pred_genes] = 1
+    pred_mask = None
+    pc = np.asarray(pred_cells, dtype=np.int64)
+    if pc.size != ncells or (pc != np.arange(ncells)).any():
+        pred_mask = np.zeros(ncells, dtype=np.int32)
+        pred_mask[pc] = 1
+    common = dict(self_col_of=self_col_of, is_pred_of=is_pred_of, pred_mask=pred_mask,
+                  npred_cells=np.unique(pc).size, nfolds=nfolds, fold_seed=fold_seed,
+                  fold_method=fold_method)
+
+    def finish(done):
+        if done != ngenes:
+            ind6 = ind[npred:ngenes]
+            msg("Estimating remaining %d genes." % ind6.size)
+            fit.run(ind6, 0, 0.0, None, False, **common)
+        if gather:
+            fit.gather()
+        info["total.time"] = time.time() - st
+        return dict(estimate=fit.est, se=fit.se, info=info, mu=fit.mu, status=fit.status,
+                    seed_of=fit.seed_of)
+
+    if npred == 0:
+        return finish(0)
+    if do_fast and not null_model:
+        n1 = min(max(8, nworkers), npred)
+        msg("Estimating finish time...")
+        fit.run(ind[:n1], 1, 0.0, None, True, **common)
+        n2 = min(max(100, nworkers), npred)
+        if n1 == npred:
+            return finish(n1)
+        msg("Calculating max cor cutoff...")
+        fit.run(ind[n1:n2], 1, 0.0, None, True, **common)
+        b = _lm(np.sqrt(info["sd.cv"][ind[:n2]]), info["maxcor"][ind[:n2]])
+        cutoff = float((0.5 - b[0]) / b[1])
+        info["cutoff"] = cutoff
+        perc = float(np.mean(info["maxcor"][ind[:n2]] > cutoff))
+        n3 = npred if perc <= 0 else min(max(int(np.ceil(n2 / perc)), nworkers) + n2, npred)
+        if n2 == npred:
+            return finish(n2)
+        msg("Calculating lambda coefficients...")
+        fit.run(ind[n2:n3], 1, cutoff, None, True, **common)
+        if n3 == npred:
+            return finish(n3)
+        pred = np.where(info["maxcor"] > cutoff)[0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = np.log(info["lambda.max"][pred] / info["lambda.min"][pred]) ** 2
+        coefs = _lm(z, info["maxcor"][pred])
+        info["lambda.coefs"] = coefs
+        cutoff2 = max(cutoff, float(-coefs[0] / coefs[1]))
+        n4 = min(max(int(np.ceil((npred - n3) / 4)), nworkers) + n3, npred)
+        msg("Predicting remaining genes...")
+        fit.run(ind[n3:n4], 2, cutoff2, coefs, True, **common)
+        if n4 == npred:
+            return finish(n4)
+        msg("Predicting remaining genes...")
+        fit.run(ind[n4:npred], 2, cutoff2, coefs, True, **common)
+        return finish(npred)
+    mode = 0 if null_model else 1
+    # the slow schedule: n1, a quarter of the rest, the rest -- all cross-validated, maxcor = 2
+    n1 = min(max(8, nworkers), npred)
+    msg("Estimating finish time...")
+    fit.run(ind[:n1], mode, 0.0, None, False, **common)
+    if n1 == npred:
+        return finish(n1)
+    n2 = min(int(np.ceil((npred - n1) / 4)) + n1, npred)
+    msg("Predicting remaining genes...")
+    fit.run(ind[n1:n2], mode, 0.0, None, False, **common)
+    if n2 == npred:
+        return finish(n2)
+    msg("Predicting remaining genes...")
+    fit.run(ind[n2:npred], mode, 0.0, None, False, **common)
+    return finish(npred)
+
+
+def _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, block):
+    """Shared body of saver.fit.mean / saver.fit.null: calc.post on a supplied prediction."""
+    ngenes, ncells = x.shape
+    est = np.zeros((ngenes, ncells))
+    se = None if estimates_only else np.zeros((ngenes, ncells))
+    z = lambda: np.zeros(ngenes)  # noqa: E731
+    info = {"size.factor": scale_sf * sf, "maxcor": z(), "lambda.max": z(), "lambda.min": z(),
+            "sd.cv": z(), "pred.time": z(), "var.time": z(), "cutoff": 0.0, "lambda.coefs": 0.0,
+            "total.time": 0.0}
+    st = time.time()
+    h = backend.handle
+    for b0 in range(0, ngenes, block):
+        rows = np.arange(b0, min(ngenes, b0 + block))
+        xb = _dense_rows(x, rows)
+        t0 = time.time()
+        r = ops.calc_post(xb, mu_rows(rows, xb), sf, scale_sf, want_se=not estimates_only,
+                          want_info=False, handle=h)
+        est[rows] = r["est"]
+        if se is not None:
+            se[rows] = r["se"]
+        info["var.time"][rows] = (time.time() - t0) / rows.size
+    info["total.time"] = time.time() - st
+    return dict(estimate=est, se=se, info=info, mu=None, status=np.zeros(ngenes, dtype=np.int32))
+
+
+def saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only=False, backend=None, comm=None):
+    """saver.fit.mean (R/saver_fit.R:467-538) + calc.estimate.mean (R/calc_estimate.R:166-221):
+    the user's mu, rescaled per gene to the mean of y, zero rows patched with the gene mean."""
+    backend = backend or CudaBackend(comm=comm)
+
+    def mu_rows(rows, xb):
+        y = xb / sf
+        imu = np.array(mu[rows], dtype=np.float64, copy=True)
+        gm, mm = y.mean(1), imu.mean(1)
+        imu[mm == 0] = gm[mm == 0][:, None]
+        return imu * (y.mean(1) / imu.mean(1))[:, None]
+
+    return _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, backend.block)
+
+
+def saver_fit_null(x, ncores, sf, scale_sf, estimates_only=False, backend=None, comm=None):
+    """saver.fit.null (R/saver_fit.R:542-628) + calc.estimate.null (R/calc_estimate.R:226-277)."""
+    backend = backend or CudaBackend(comm=comm)
+    return _fit_given_mu(x, sf, scale_sf, lambda rows, xb: (xb / sf).mean(1), estimates_only,
+                         backend, comm, backend.block)
+
+
+def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=None,
+          pred_genes=None, pred_genes_only=False, null_model=False, mu=None,
+          estimates_only=False, *, gene_names=None, cell_names=None, backend=None, comm=None,
+          perm="identity", fold_seed=0, fold_method="philox", nfolds=5, return_mu=False,
+          verbose=False):
+    """saver() (R/saver.R:98-179).  x: genes x cells counts (numpy array or scipy.sparse).
+
+    pred_cells / pred_genes are 0-based.  ``ncores`` is accepted for signature compatibility;
+    device parallelism (one process per GPU, ``comm``) replaces the PSOCK workers.  Returns a
+    SaverResult (or the estimate matrix when ``estimates_only``), exactly as the reference."""
+    msg = (lambda s: print(s, flush=True)) if verbose else (lambda s: None)
+    if mu is not None:
+        mu = check_mu(x, mu)
+    x, kept = clean_data(x)
+    if cell_names is not None:
+        cell_names = np.asarray(cell_names)[kept]
+    ngenes, ncells = x.shape
+    if gene_names is None:
+        gene_names = np.arange(1, ngenes + 1)
+    msg("%d genes, %d cells" % (ngenes, ncells))
+    sf, scale_sf = calc_size_factor(x, size_factor, ncells)
+    backend = backend or CudaBackend(comm=comm)
+    if mu is not None:
+        out = saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only, backend, comm)
+    elif null_model:
+        out = saver_fit_null(x, ncores, sf, scale_sf, estimates_only, backend, comm)
+    else:
+        pc = get_pred_cells(pred_cells, ncells)
+        pg = get_pred_genes(x, pred_genes, npred, ngenes)
+        rm = np.asarray(x.mean(1)).ravel()
+        good = np.where(rm >= 0.1)[0]
+        # x.est = t(log((x[good, ] + 1) / sf))  (R/saver.R:156-157), kept gene-major: (p, n)
+        x_est = np.log((_dense_rows(x, good) + 1.0) / sf)
+        # the x.est column carrying each gene's own name (R/calc_estimate.R:103), -1 if none
+        self_col = np.full(ngenes, -1, dtype=np.int32)
+        self_col[good] = np.arange(good.size, dtype=np.int32)
+        if pred_genes_only:
+            x = x[pg]
+            gene_names = np.asarray(gene_names)[pg]
+            self_col = self_col[pg]
+            pg = np.arange(x.shape[0])
+        out = saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pg, pc, null_model,
+                        estimates_only=estimates_only, self_col=self_col, backend=backend,
+                        comm=comm, perm=perm, fold_seed=fold_seed, fold_method=fold_method,
+                        nfolds=nfolds, keep_mu=return_mu, messages=msg)
+    msg("Done!")
+    res = SaverResult(out["estimate"], out["se"], out["info"], out.get("mu"), gene_names,
+                      cell_names)
+    res.status = out.get("status")
+    res.seed_of = out.get("seed_of")
+    res.x, res.sf, res.scale_sf = x, sf, scale_sf
+    if estimates_only and not return_mu:
+        return res.estimate
+    return res

@@ -197,3 +197,42 @@ def predict_path(Y, lambda_max, lambda_min, self_col=None, pred_mask=None, dfmax
                                           int(dfmax), _D(float(thresh)), ptr(mu), ptr(status),
                                           ptr(stats), int(dev)))
     return dict(mu=mu, status=status, stats=stats)
+
+
+def calc_estimate(x, sf, scale_sf, mode, cutoff=0.0, coefs=None, self_col=None, is_pred=None,
+                  pred_mask=None, foldid=None, nfolds=5, calc_maxcor=False, want_se=True,
+                  want_mu=False, dfmax=300, nlambda=100, thresh=1e-7, handle=None):
+    """calc.estimate body (R/calc_estimate.R:75-141) for one block: x (B, n) raw counts.
+
+    mode 0 null.model / 1 cross-validated lasso / 2 est.lambda + fixed-lambda path.
+    Returns dict(est, se, maxcor, lambda_max, lambda_min, sd_cv, ct, vt, status[, mu])."""
+    h = handle or default_handle()
+    dev = is_device(x)
+    if dev:
+        import torch
+        B, n = x.shape
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=x.device)  # noqa: E731
+        f64, i32 = torch.float64, torch.int32
+    else:
+        x = _f64(np.atleast_2d(x))
+        B, n = x.shape
+        sf = _f64(np.broadcast_to(_vec(sf, n), (n,)))
+        self_col = None if self_col is None else _i32(self_col)
+        is_pred = None if is_pred is None else _i32(is_pred)
+        pred_mask = None if pred_mask is None else _i32(pred_mask)
+        foldid = None if foldid is None else _i32(foldid).reshape(B, n)
+        mk = lambda shape, dt: np.empty(shape, dtype=dt)  # noqa: E731
+        f64, i32 = np.float64, np.int32
+    cf = None if coefs is None else _f64(np.asarray(coefs, dtype=np.float64))
+    est = mk((B, n), f64)
+    se = mk((B, n), f64) if want_se else None
+    info = mk((6, B), f64)
+    mu = mk((B, n), f64) if want_mu else None
+    status = mk((B,), i32)
+    h.check(h.lib.saver_cuda_calc_estimate(
+        h.h, ptr(x), n, B, ptr(sf), _D(float(scale_sf)), ptr(self_col), ptr(is_pred),
+        ptr(pred_mask), ptr(foldid), int(nfolds), int(mode), int(bool(calc_maxcor)),
+        _D(float(cutoff)), ptr(cf), int(dfmax), int(nlambda), _D(float(thresh)), ptr(est), ptr(se),
+        ptr(info), ptr(mu), ptr(status), int(dev)))
+    return dict(est=est, se=se, maxcor=info[0], lambda_max=info[1], lambda_min=info[2],
+                sd_cv=info[3], ct=info[4], vt=info[5], status=status, mu=mu)

@@ -7,13 +7,16 @@ mean N(-1, 1.5^2), cell depth LogNormal(0, 0.35^2), dispersion Gamma(2, 1) clipp
 import numpy as np
 
 
-def nb_counts(n_genes, n_cells, seed, k=12):
-    rng = np.random.default_rng(seed)
-    Z = rng.standard_normal((n_cells, k))
+def nb_counts(n_genes, n_cells, seed, k=12, gene_stream=0):
+    """gene_stream > 0 draws a different block of genes over the SAME cells (same latent factors
+    and depths), which is how bench.py gives every GPU its own block against one shared design."""
+    cell_rng = np.random.default_rng([seed, 0])
+    Z = cell_rng.standard_normal((n_cells, k))
+    depth = cell_rng.lognormal(0.0, 0.35, n_cells)
+    rng = np.random.default_rng([seed, 1 + gene_stream])
     W = rng.normal(0.0, 0.5, (n_genes, k))
     W[rng.random(n_genes) < 0.3] = 0.0
     b = rng.normal(-1.0, 1.5, n_genes)
-    depth = rng.lognormal(0.0, 0.35, n_cells)
     phi = np.clip(rng.gamma(2.0, 1.0, n_genes), 0.1, 50.0)
     out = np.empty((n_genes, n_cells), dtype=np.int32)
     step = max(1, (1 << 24) // max(n_cells, 1))

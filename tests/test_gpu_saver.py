@@ -1,0 +1,106 @@
+"""GPU end-to-end: saver() through the host mirror + libsaver_cuda vs the CPU oracle pipeline
+on identical inputs and folds (acceptance #2 of BASELINE.md: median relative error <= 1e-3,
+per-gene Spearman >= 0.999), and vs the reference's stored linnarsson_saver object."""
+import numpy as np
+import pytest
+from scipy.stats import spearmanr
+
+import oracle
+import saver_b200
+from saver_b200 import host, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def _oracle_gene(res, x_est, good, g, fold_seed, nfolds=5):
+    """expr.predict (CV) + calc.post for gene g with the folds saver() used."""
+    n = res.x.shape[1]
+    y = res.x[g] / res.sf
+    fold = host.draw_folds([int(res.seed_of[g])], n, nfolds, fold_seed)[0]
+    excl = int(np.where(good == g)[0][0]) if g in good else -1
+    r = oracle.predict_cv(x_est, y, fold, excl=excl)
+    post = oracle.calc_post(res.x[g], r["mu"], res.sf, res.scale_sf)
+    return r, post
+
+
+def test_saver_full_cv_matches_oracle(handle):
+    x = synth.nb_counts(140, 240, seed=7)
+    res = saver_b200.saver(x, do_fast=False, fold_seed=11, return_mu=True,
+                           backend=host.CudaBackend(handle=handle))
+    assert res.estimate.shape == x.shape and np.isfinite(res.estimate).all()
+    xc = res.x
+    good = np.where(xc.mean(1) >= 0.1)[0]
+    x_est = np.log((xc[good] + 1.0) / res.sf)
+    pred = np.where(xc.sum(1) > 0)[0]
+    med, rho, same = [], [], []
+    for g in pred[::5]:
+        r, post = _oracle_gene(res, x_est, good, g, 11)
+        assert res.status[g] == r["rc"]
+        if r["rc"] == 0:
+            same.append(abs(res.info["lambda.min"][g] - r["lambda_min"]) < 1e-12 * r["lambda_min"])
+            assert abs(res.info["lambda.max"][g] - r["lambda_max"]) < 1e-10 * r["lambda_max"]
+        med.append(np.median(_rel(res.estimate[g], post["est"])))
+        if np.ptp(post["est"]) > 0:
+            rho.append(spearmanr(res.estimate[g], post["est"])[0])
+    assert np.median(med) <= 1e-3, np.median(med)
+    assert np.mean(same) > 0.85
+    assert np.median(rho) >= 0.999
+    # all-zero genes: zero estimate; info of non-predicted genes is zero
+    zero = np.where(xc.sum(1) == 0)[0]
+    assert (res.estimate[zero] == 0).all()
+
+
+def test_saver_fast_schedule_on_linnarsson_vs_golden(golden, handle):
+    """do.fast=TRUE on the reference's bundled data.  The stored object used another random gene
+    order and other folds, so stage membership differs; what must agree: maxcor exactly, the
+    lambda regression and cutoff in distribution, estimates to a few percent."""
+    x = golden["counts"].astype(np.float64)
+    res = saver_b200.saver(x, do_fast=True, perm=1, fold_seed=2,
+                           backend=host.CudaBackend(handle=handle))
+    info = res.info
+    done = info["maxcor"] > 0
+    assert np.abs(info["maxcor"][done] - golden["maxcor"][done]).max() < 1e-12
+    assert abs(info["cutoff"] - golden["cutoff"][0]) < 0.08
+    assert np.abs(np.asarray(info["lambda.coefs"]) - golden["lambda_coefs"]).max() < 3.0
+    gold = golden["estimate_m"] / 1000.0
+    rel = _rel(res.estimate, gold)
+    assert np.median(rel) < 0.02, np.median(rel)
+    # genes that both runs treated as null (mean prediction, no stochastic branch) agree exactly
+    both_null = (info["lambda.max"] == 0) & (golden["lambda_max"] == 0)
+    exact = (np.rint(res.estimate[both_null] * 1000) == golden["estimate_m"][both_null]).all(1)
+    assert both_null.sum() > 300 and exact.mean() > 0.85
+    se_rel = _rel(res.se, golden["se_m"] / 1000.0)
+    assert np.median(se_rel) < 0.03
+
+
+def test_saver_null_model_mu_and_arguments(handle):
+    x = synth.nb_counts(60, 150, seed=3).astype(np.float64)
+    be = host.CudaBackend(handle=handle)
+    # null.model = TRUE: calc.b on the gene mean (R/calc_estimate.R:226-277)
+    res = saver_b200.saver(x, null_model=True, backend=be)
+    g = int(np.argmax(res.x.sum(1)))
+    y = res.x[g] / res.sf
+    post = oracle.calc_post(res.x[g], np.full(y.size, y.mean()), res.sf, res.scale_sf)
+    assert _rel(res.estimate[g], post["est"]).max() < 1e-9
+    # mu supplied (R/calc_estimate.R:166-221): rescaled to the gene mean
+    rng = np.random.default_rng(0)
+    mu = res.x.mean(1, keepdims=True) * np.exp(0.3 * rng.standard_normal(res.x.shape))
+    res2 = saver_b200.saver(res.x, mu=mu, backend=be)
+    pm = mu[g] * (y.mean() / mu[g].mean())
+    post2 = oracle.calc_post(res.x[g], pm, res.sf, res.scale_sf)
+    assert _rel(res2.estimate[g], post2["est"]).max() < 1e-6
+    # estimates.only returns the bare matrix; size.factor vector rescales the output
+    est = saver_b200.saver(x, null_model=True, estimates_only=True, backend=be)
+    assert isinstance(est, np.ndarray) and np.array_equal(est, res.estimate)
+    with pytest.raises(saver_b200.SaverError):
+        saver_b200.saver(x, size_factor=np.array([1.0, 2.0]), backend=be)
+    with pytest.raises(saver_b200.SaverError):
+        saver_b200.saver(x[:, :1], backend=be)
+    # pred.genes + pred.genes.only + pred.cells run and return only the requested rows
+    sub = saver_b200.saver(x, do_fast=False, pred_genes=np.arange(10), pred_genes_only=True,
+                           pred_cells=np.arange(0, x.shape[1], 2), backend=be)
+    assert sub.estimate.shape[0] == 10 and np.isfinite(sub.estimate).all()
