@@ -164,6 +164,13 @@ SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);
  * initial gradient), [3] variance/posterior kernel inside calc_estimate, [4] design columns the
  * round kernels streamed (n x 8 bytes each), [5] GEMM problem columns, [6] rounds, [7] launches. */
 SAVER_API int saver_cuda_counters(saver_cuda_handle h, double* out8);
+/* [0] sum of round-kernel CTA lifetimes (SM cycles), [1] the longest single CTA; [2..3] reserved */
+SAVER_API int saver_cuda_counters_ext(saver_cuda_handle h, double* out4);
+
+/* Diagnostics: the master path of gene g of the LAST block the solver ran -- per lambda (128
+ * slots) intercept, deviance ratio, ever-active count, cumulative sweeps, lambda. */
+SAVER_API int saver_cuda_debug_path(saver_cuda_handle h, int g, double* a0, double* dev, int* nin,
+                                    int* nlp, double* lam);
 
 #ifdef __cplusplus
 }

@@ -501,6 +501,14 @@ typedef struct {
  * Outputs: a0[nlam], ca[nx*nlam] (compressed coefs on standardised scale),
  * ia[nx] (0-based column of compressed slot), kin[nlam], dev[nlam], alm[nlam].
  */
+/* diagnostics (single-threaded use only): per-lambda sweep / gradient-pass counters of the last fit */
+static int dbg_nlp[128], dbg_ngrad[128], dbg_nin[128];
+ORC_API void orc_debug_last_fit(int *nlp, int *ngrad, int *nin)
+{
+    memcpy(nlp, dbg_nlp, sizeof dbg_nlp); memcpy(ngrad, dbg_ngrad, sizeof dbg_ngrad);
+    memcpy(nin, dbg_nin, sizeof dbg_nin);
+}
+
 static void fishnet1(int m, int p, const double *xs, const int *ju, const double *y, int nlam,
                      double flmin, const double *ulam, int ne, int nx, double thr, int maxit,
                      double *a0, double *ca, int *ia, int *kin, double *dev, double *alm,
@@ -660,6 +668,7 @@ static void fishnet1(int m, int p, const double *xs, const int *ju, const double
         if (overflow) { fi->jerr = -10000 - (ilm + 1); break; }
         for (int l = 0; l < nin; ++l) ca[(size_t)ilm * nx + l] = a[ia[l]];
         kin[ilm] = nin;
+        if (ilm < 128) { dbg_nlp[ilm] = nlp; dbg_ngrad[ilm] = fi->ngrad; dbg_nin[ilm] = nin; }
         a0[ilm] = az;
         alm[ilm] = al;
         fi->lmu = ilm + 1;

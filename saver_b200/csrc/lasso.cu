@@ -27,6 +27,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "saver_kernels.h"
@@ -74,8 +75,13 @@ __device__ __forceinline__ void bsum(double (&v)[K], double* buf, int& phase) {
     if (lane == 0) b[k * 32 + warp] = v[k];
   }
   __syncthreads();
+  // second stage: every group of nw lanes holds all nw partials, log2(nw) butterfly levels
 #pragma unroll
-  for (int k = 0; k < K; ++k) v[k] = warp_sum(lane < nw ? b[k * 32 + lane] : 0.0);
+  for (int k = 0; k < K; ++k) {
+    double t = b[k * 32 + (lane & (nw - 1))];
+    for (int o = nw >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    v[k] = t;
+  }
   phase ^= 1;
 }
 
@@ -93,6 +99,14 @@ __device__ __forceinline__ double bmax(double v, double* buf, int& phase) {
 __device__ __forceinline__ double2 ldg2(const double* p) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
+
+__device__ __forceinline__ void cpa16(void* smem, const void* gmem) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(a), "l"(gmem));
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -270,7 +284,8 @@ __global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
 // ---------------------------------------------------------------------------------------------
 // the round kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int kFixedSmem = 256 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4;
+constexpr int kMeta = 64;  // strong-set metadata staged per chunk
+constexpr int kFixedSmem = 256 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4 + kMeta * (8 + 8 + 4 + 4) + 16;
 
 template <int T>
 __device__ __forceinline__ int rebuild_strong(const int* MMc, int* SIc, int p, int* ish) {
@@ -295,7 +310,10 @@ __device__ __forceinline__ int rebuild_strong(const int* MMc, int* SIc, int p, i
   return base;
 }
 
-template <int T, bool STAGED>
+// STAGED: working weights / residual live in shared memory.  XBUF: design columns are streamed
+// through a two-deep cp.async ring in shared memory, so the L2 latency of column l+1 hides behind
+// the reduction of column l and the axpy re-reads the column from shared memory.
+template <int T, bool STAGED, bool XBUF>
 __global__ void __launch_bounds__(T)
 lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ nextlist,
                    int* __restrict__ counter) {
@@ -309,12 +327,19 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   double* xia = xma + kNX;
   int* ia = reinterpret_cast<int*>(xia + kNX);
   int* ish = ia + kNX;
-  double* wv = reinterpret_cast<double*>(ish + 64);
+  double* mxm = reinterpret_cast<double*>(ish + 64);   // staged strong-set metadata
+  double* mxi = mxm + kMeta;
+  int* mk = reinterpret_cast<int*>(mxi + kMeta);
+  int* mpos = mk + kMeta + 4;  // mk has one extra slot: first column of the next chunk
+  double* wv = reinterpret_cast<double*>(mpos + kMeta);
   double* wrv = wv + A.ldx;
+  double* xb0 = wrv + A.ldx;  // XBUF only
+  double* xb1 = xb0 + A.ldx;
 
   const int tid = threadIdx.x;
   int phase = 0;
   unsigned ncols = 0;  // design columns this CTA streamed (roofline accounting)
+  const long long t_start = clock64();
   const int pid = list[blockIdx.x];
   LassoProb* PR = A.ws.prob + pid;
   const int g = PR->gene, fit = PR->fit, slot = PR->slot;
@@ -425,6 +450,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
           A.ws.a0p[o] = az;
           A.ws.devp[o] = cur_dev;
           A.ws.ninp[o] = nin;
+          A.ws.nlpp[o] = nlp;
         }
         double* cp = A.ws.cap + o * kNX;
         for (int l = tid; l < nin; l += T) cp[l] = aact[l];
@@ -484,11 +510,26 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
     }
     sumr = s[0] - d * v0;
   };
-  auto axpy = [&](const double* col, double d, double xm, double xi) {
+  // column access: the thread that copies element i is the only one that reads it back, so a
+  // cp.async.wait_group is all the synchronisation the ring needs
+  auto col_issue = [&](int k, double* xb) {
+    const double* col = Xs + (size_t)k * ldx;
+    if (XBUF) {
+      for (int i = 2 * tid; i < ldx; i += 2 * T) cpa16(xb + i, col + i);
+      cpa_commit();
+    } else if ((tid & 7) == 0) {
+      for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(col + i);
+    }
+  };
+  auto ldx2 = [&](const double* base, int i) -> double2 {
+    if (XBUF) return *reinterpret_cast<const double2*>(base + i);
+    return ldg2(base + i);
+  };
+  auto axpy = [&](const double* xc, double d, double xm, double xi) {
     const double c = d * xi;
 #pragma unroll 2
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
-      const double2 x = ldg2(col + i);
+      const double2 x = ldx2(xc, i);
       double2 r = *reinterpret_cast<const double2*>(wrv + i);
       const double2 w = *reinterpret_cast<const double2*>(wv + i);
       r.x -= c * w.x * (x.x - xm);
@@ -505,66 +546,87 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
       while (true) {  // sweeps over the strong set until one changes nothing
         ++nlp;
         double dlx = 0.0;
-        if (nS > 0 && (tid & 7) == 0) {
-          const double* c0 = Xs + (size_t)SIc[0] * ldx;
-          for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(c0 + i);
-        }
         ncols += nS;
-        for (int s = 0; s < nS; ++s) {
-          const int k = SIc[s];
-          const double* col = Xs + (size_t)k * ldx;
-          if (s + 1 < nS && (tid & 7) == 0) {
-            const double* cn = Xs + (size_t)SIc[s + 1] * ldx;
-            for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(cn + i);
+        int buf = 0;
+        if (nS > 0) col_issue(SIc[0], xb0);
+        for (int s0 = 0; s0 < nS && !overflow && !nanfail; s0 += kMeta) {
+          const int cn = nS - s0 < kMeta ? nS - s0 : kMeta;
+          __syncthreads();  // previous chunk's metadata fully consumed
+          if (tid < cn) {
+            const int k = SIc[s0 + tid];
+            mk[tid] = k;
+            mxm[tid] = XMc[k];
+            mxi[tid] = XIc[k];
+            mpos[tid] = MMc[k];
+          } else if (tid == cn && s0 + cn < nS) {
+            mk[cn] = SIc[s0 + cn];  // first column of the next chunk, for the prefetch
           }
-          int pos = MMc[k];
-          const double xm = XMc[k], xi = XIc[k];
-          const double ak = pos > 0 ? aact[pos - 1] : 0.0;  // read before the reduction's barrier
-          double d3[3] = {0.0, 0.0, 0.0};
-#pragma unroll 2
-          for (int i = 2 * tid; i < ldx; i += 2 * T) {
-            const double2 x = ldg2(col + i);
-            const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-            const double2 w = *reinterpret_cast<const double2*>(wv + i);
-            d3[0] += r.x * x.x + r.y * x.y;
-            const double wx0 = w.x * x.x, wx1 = w.y * x.y;
-            d3[1] += wx0 + wx1;
-            d3[2] += wx0 * x.x + wx1 * x.y;
-          }
-          bsum<3>(d3, red, phase);
-          const double sw = xi * (d3[1] - xm * v0);
-          const double v = xi * xi * (d3[2] - 2.0 * xm * d3[1] + xm * xm * v0);
-          const double gk = xi * (d3[0] - xm * sumr);
-          const double u = gk + v * ak;
-          const double au = fabs(u) - al;
-          const double anew = au > 0.0 ? copysign(au, u) / v : 0.0;
-          if (pos > 0 && tid == 0) {
-            va[pos - 1] = v;
-            swa[pos - 1] = sw;
-          }
-          if (anew == ak) continue;
-          if (anew != anew) { nanfail = true; break; }
-          const double d = anew - ak;
-          dlx = fmax(dlx, v * d * d);
-          axpy(col, d, xm, xi);
-          sumr -= d * sw;
-          if (pos < 0) {
-            ++nin;
-            if (nin > nx) { overflow = true; break; }
-            pos = nin;
-            if (tid == 0) {
-              MMc[k] = nin;
-              ia[nin - 1] = k;
-              xma[nin - 1] = xm;
-              xia[nin - 1] = xi;
-              va[nin - 1] = v;
-              swa[nin - 1] = sw;
-              as_[nin - 1] = 0.0;
+          __syncthreads();
+          for (int j = 0; j < cn; ++j) {
+            const int k = mk[j];
+            double* xcur = buf ? xb1 : xb0;
+            if (s0 + j + 1 < nS) {
+              col_issue(mk[j + 1], buf ? xb0 : xb1);
+              if (XBUF) cpa_wait<1>();
+            } else if (XBUF) {
+              cpa_wait<0>();
             }
+            const double* xc = XBUF ? xcur : Xs + (size_t)k * ldx;
+            buf ^= 1;
+            int pos = mpos[j];
+            const double xm = mxm[j], xi = mxi[j];
+            const double ak = pos > 0 ? aact[pos - 1] : 0.0;  // read before the reduction's barrier
+            double d3[3] = {0.0, 0.0, 0.0}, e3[3] = {0.0, 0.0, 0.0};
+#pragma unroll 2
+            for (int i = 2 * tid; i < ldx; i += 2 * T) {
+              const double2 x = ldx2(xc, i);
+              const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+              const double2 w = *reinterpret_cast<const double2*>(wv + i);
+              d3[0] += r.x * x.x;
+              e3[0] += r.y * x.y;
+              const double wx0 = w.x * x.x, wx1 = w.y * x.y;
+              d3[1] += wx0;
+              e3[1] += wx1;
+              d3[2] += wx0 * x.x;
+              e3[2] += wx1 * x.y;
+            }
+            d3[0] += e3[0]; d3[1] += e3[1]; d3[2] += e3[2];
+            bsum<3>(d3, red, phase);
+            const double sw = xi * (d3[1] - xm * v0);
+            const double v = xi * xi * (d3[2] - 2.0 * xm * d3[1] + xm * xm * v0);
+            const double gk = xi * (d3[0] - xm * sumr);
+            const double u = gk + v * ak;
+            const double au = fabs(u) - al;
+            const double anew = au > 0.0 ? copysign(au, u) / v : 0.0;
+            if (pos > 0 && tid == 0) {
+              va[pos - 1] = v;
+              swa[pos - 1] = sw;
+            }
+            if (anew == ak) continue;
+            if (anew != anew) { nanfail = true; break; }
+            const double d = anew - ak;
+            dlx = fmax(dlx, v * d * d);
+            axpy(xc, d, xm, xi);
+            sumr -= d * sw;
+            if (pos < 0) {
+              ++nin;
+              if (nin > nx) { overflow = true; break; }
+              pos = nin;
+              if (tid == 0) {
+                MMc[k] = nin;
+                ia[nin - 1] = k;
+                xma[nin - 1] = xm;
+                xia[nin - 1] = xi;
+                va[nin - 1] = v;
+                swa[nin - 1] = sw;
+                as_[nin - 1] = 0.0;
+              }
+            }
+            if (tid == 0) aact[pos - 1] = anew;
+            // aact / va are next read after at least one __syncthreads (the next bsum)
           }
-          if (tid == 0) aact[pos - 1] = anew;
-          // aact / va are next read after at least one __syncthreads (the next bsum)
         }
+        if (XBUF) cpa_wait<0>();
         if (overflow || nanfail) break;
         intercept_update(dlx);
         if (dlx < shr) break;
@@ -574,21 +636,29 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
           ++nlp;
           dlx = 0.0;
           ncols += nin;
+          buf = 0;
+          if (nin > 0) col_issue(ia[0], xb0);
           for (int l = 0; l < nin; ++l) {
             const int k = ia[l];
-            const double* col = Xs + (size_t)k * ldx;
-            if (l + 1 < nin && (tid & 7) == 0) {
-              const double* cn = Xs + (size_t)ia[l + 1] * ldx;
-              for (int i = 2 * tid; i < ldx; i += 2 * T) prefetch_l1(cn + i);
+            double* xcur = buf ? xb1 : xb0;
+            if (l + 1 < nin) {
+              col_issue(ia[l + 1], buf ? xb0 : xb1);
+              if (XBUF) cpa_wait<1>();
+            } else if (XBUF) {
+              cpa_wait<0>();
             }
+            const double* xc = XBUF ? xcur : Xs + (size_t)k * ldx;
+            buf ^= 1;
             const double xm = xma[l], xi = xia[l], v = va[l], ak = aact[l], sw = swa[l];
-            double d1[1] = {0.0};
+            double d1[1] = {0.0}, e1 = 0.0;
 #pragma unroll 2
             for (int i = 2 * tid; i < ldx; i += 2 * T) {
-              const double2 x = ldg2(col + i);
+              const double2 x = ldx2(xc, i);
               const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-              d1[0] += r.x * x.x + r.y * x.y;
+              d1[0] += r.x * x.x;
+              e1 += r.y * x.y;
             }
+            d1[0] += e1;
             bsum<1>(d1, red, phase);
             const double gk = xi * (d1[0] - xm * sumr);
             const double u = gk + v * ak;
@@ -598,10 +668,11 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
             if (anew != anew) { nanfail = true; break; }
             const double d = anew - ak;
             dlx = fmax(dlx, v * d * d);
-            axpy(col, d, xm, xi);
+            axpy(xc, d, xm, xi);
             sumr -= d * sw;
             if (tid == 0) aact[l] = anew;  // all reads of aact[l] precede the reduction's barrier
           }
+          if (XBUF) cpa_wait<0>();
           if (nanfail) break;
           intercept_update(dlx);
           if (dlx < shr) break;
@@ -708,6 +779,10 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   }
   if (tid == 0) {
     atomicAdd(A.ws.colcount, (unsigned long long)ncols);
+    const unsigned long long cyc = (unsigned long long)(clock64() - t_start);
+    atomicAdd(A.ws.colcount + 1, cyc);   // sum of CTA lifetimes
+    atomicMax(A.ws.colcount + 2, cyc);   // longest CTA of the block of rounds (straggler)
+    atomicAdd(A.ws.colcount + 3, (unsigned long long)(state == ST_WAIT_KKT || state == ST_DONE));
     if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
     PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
     PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
@@ -873,22 +948,22 @@ __global__ void __launch_bounds__(256) lasso_finalize_kernel(FinalArgs F) {
   if (tid == 0) F.status[g] = 0;
 }
 
+template <int T, bool STAGED, bool XBUF>
+cudaError_t launch_round_k(const RoundArgs& A, const int* list, int* nextlist, int* counter,
+                           int grid, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(lasso_round_kernel<T, STAGED, XBUF>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lasso_round_kernel<T, STAGED, XBUF><<<grid, T, smem, s>>>(A, list, nextlist, counter);
+  return cudaGetLastError();
+}
+
 template <int T>
 cudaError_t launch_round_t(const RoundArgs& A, const int* list, int* nextlist, int* counter,
-                           int grid, bool staged, size_t smem, cudaStream_t s) {
-  cudaError_t e;
-  if (staged) {
-    e = cudaFuncSetAttribute(lasso_round_kernel<T, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    lasso_round_kernel<T, true><<<grid, T, smem, s>>>(A, list, nextlist, counter);
-  } else {
-    e = cudaFuncSetAttribute(lasso_round_kernel<T, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    lasso_round_kernel<T, false><<<grid, T, smem, s>>>(A, list, nextlist, counter);
-  }
-  return cudaGetLastError();
+                           int grid, int mode, size_t smem, cudaStream_t s) {
+  if (mode == 2) return launch_round_k<T, true, true>(A, list, nextlist, counter, grid, smem, s);
+  if (mode == 1) return launch_round_k<T, true, false>(A, list, nextlist, counter, grid, smem, s);
+  return launch_round_k<T, false, false>(A, list, nextlist, counter, grid, smem, s);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -896,7 +971,9 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 int lasso_max_block(int NF) {
-  int b = 3072 / NF;
+  int tot = 6144;  // problems in flight per block: enough waves to even out uneven problems
+  if (const char* e = getenv("SAVER_LASSO_PROBLEMS")) tot = atoi(e);
+  int b = tot / NF;
   return b < 1 ? 1 : b;
 }
 
@@ -921,7 +998,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oPR = take(sizeof(LassoProb) * (size_t)P), oLam = take((size_t)kNLam * B * 8),
                oNl = take((size_t)B * 4), oLf = take((size_t)B * 4), oGs = take((size_t)B * 4),
                oGm = take((size_t)B * 8), oA0 = take((size_t)kNLam * B * 8),
-               oDv = take((size_t)kNLam * B * 8), oNi = take((size_t)kNLam * B * 4),
+               oDv = take((size_t)kNLam * B * 8), oNi = take((size_t)kNLam * B * 4), oNp = take((size_t)kNLam * B * 4),
                oCap = take((size_t)kNX * kNLam * B * 8),
                oCv = take((size_t)kNLam * kMaxFolds * B * 8), oL0 = take((size_t)P * 4),
                oL1 = take((size_t)P * 4), oCt = take(64), oCc = take(64);
@@ -944,7 +1021,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   ws.AACT = (double*)(b + oAA); ws.prob = (LassoProb*)(b + oPR); ws.lam = (double*)(b + oLam);
   ws.nlam_g = (int*)(b + oNl); ws.Lfinal = (int*)(b + oLf); ws.gstat = (int*)(b + oGs);
   ws.gmean = (double*)(b + oGm); ws.a0p = (double*)(b + oA0); ws.devp = (double*)(b + oDv);
-  ws.ninp = (int*)(b + oNi); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
+  ws.ninp = (int*)(b + oNi); ws.nlpp = (int*)(b + oNp); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
   ws.list0 = (int*)(b + oL0); ws.list1 = (int*)(b + oL1); ws.counters = (int*)(b + oCt);
   ws.colcount = (unsigned long long*)(b + oCc);
   for (auto& ev : ws.ev)
@@ -980,10 +1057,14 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   // ---- rounds ----
-  const size_t smem_staged = kFixedSmem + (size_t)2 * ldx * 8;
-  const bool staged = smem_staged <= 227 * 1024;
-  const size_t smem = staged ? smem_staged : kFixedSmem;
-  const int T = ldx <= 512 ? 128 : ldx <= 2560 ? 256 : ldx <= 6144 ? 512 : 1024;
+  // shared-memory plan: 2 = state + column ring (two CTAs per SM must still fit), 1 = state only,
+  // 0 = everything through L2 (n too large to stage)
+  const size_t smem_x = kFixedSmem + (size_t)4 * ldx * 8, smem_s = kFixedSmem + (size_t)2 * ldx * 8;
+  const int mode = smem_x <= 113 * 1024 ? 2 : smem_s <= 227 * 1024 ? 1 : 0;
+  const size_t smem = mode == 2 ? smem_x : mode == 1 ? smem_s : kFixedSmem;
+  int T = ldx <= 2048 ? 128 : ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
+  if (const char* e = getenv("SAVER_LASSO_THREADS")) T = atoi(e);  // tuning experiments only
+  if (T != 128 && T != 256 && T != 512 && T != 1024) return cudaErrorInvalidValue;
   int cur = 0;
   cudaEventRecord(ws.ev[1], s);
   if ((e = cudaMemcpyAsync(ws.h_counter, ws.counters, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -1004,10 +1085,10 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
     cudaEventRecord(ws.ev[0], s);
     switch (T) {
-      case 128: e = launch_round_t<128>(A, list, next, cnt, live, staged, smem, s); break;
-      case 256: e = launch_round_t<256>(A, list, next, cnt, live, staged, smem, s); break;
-      case 512: e = launch_round_t<512>(A, list, next, cnt, live, staged, smem, s); break;
-      default: e = launch_round_t<1024>(A, list, next, cnt, live, staged, smem, s); break;
+      case 128: e = launch_round_t<128>(A, list, next, cnt, live, mode, smem, s); break;
+      case 256: e = launch_round_t<256>(A, list, next, cnt, live, mode, smem, s); break;
+      case 512: e = launch_round_t<512>(A, list, next, cnt, live, mode, smem, s); break;
+      default: e = launch_round_t<1024>(A, list, next, cnt, live, mode, smem, s); break;
     }
     if (e != cudaSuccess) return e;
     *launches += 1;
@@ -1037,10 +1118,12 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     }
   }
   {
-    unsigned long long cc = 0;
-    if ((e = cudaMemcpyAsync(&cc, ws.colcount, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    unsigned long long cc[4] = {0, 0, 0, 0};
+    if ((e = cudaMemcpyAsync(cc, ws.colcount, 32, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-    ws.cols_streamed += cc;
+    ws.cols_streamed += cc[0];
+    ws.cta_cycles += cc[1];
+    if (cc[2] > ws.max_cta_cycles) ws.max_cta_cycles = cc[2];
   }
   FinalArgs F;
   F.R = A; F.lmin_user = lmin_user; F.MU = MU; F.out4 = out4; F.status = status; F.stats = stats;
@@ -1048,6 +1131,18 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   lasso_finalize_kernel<<<B, 256, 0, s>>>(F);
   *launches += 1;
   return cudaGetLastError();
+}
+
+// diagnostics: master path of gene g of the last block (a0, dev, nin, sweeps per lambda)
+cudaError_t lasso_debug_path(const LassoWs& ws, int g, double* a0, double* dev, int* nin, int* nlp,
+                             double* lam) {
+  if (!ws.base) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if ((e = cudaMemcpy(a0, ws.a0p + (size_t)g * kNLam, kNLam * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(dev, ws.devp + (size_t)g * kNLam, kNLam * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(nin, ws.ninp + (size_t)g * kNLam, kNLam * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+  if ((e = cudaMemcpy(nlp, ws.nlpp + (size_t)g * kNLam, kNLam * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+  return cudaMemcpy(lam, ws.lam + (size_t)g * kNLam, kNLam * 8, cudaMemcpyDeviceToHost);
 }
 
 }  // namespace saver

@@ -64,6 +64,7 @@ struct LassoWs {
   double *gmean;             // B: mean of y over the pred cells
   double *a0p, *devp;        // kNLam x B master path
   int *ninp;                 // kNLam x B
+  int *nlpp;                 // kNLam x B sweeps so far at each commit (diagnostics)
   double *cap;               // kNX x kNLam x B master coefficients per lambda
   double *cvdev;             // kNLam x kMaxFolds x B held-out mean deviance
   int *list0, *list1;        // P each: active problem lists (ping-pong)
@@ -71,7 +72,7 @@ struct LassoWs {
   unsigned long long* colcount;  // design columns streamed by the round kernels (cumulative)
   // accounting (host side, cumulative over the handle's life)
   double ms_round = 0, ms_gemm = 0, ms_setup = 0;
-  unsigned long long cols_streamed = 0;
+  unsigned long long cols_streamed = 0, cta_cycles = 0, max_cta_cycles = 0;
   long long rounds = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void release();

@@ -385,8 +385,19 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
 
 long long saver_cuda_gemm_columns(saver_cuda_handle h) { return h ? h->gemm_cols : 0; }
 
+int saver_cuda_debug_path(saver_cuda_handle h, int g, double* a0, double* dev, int* nin, int* nlp,
+                          double* lam) {
+  if (!h) return SAVER_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(lasso_debug_path(h->lasso, g, a0, dev, nin, nlp, lam));
+  return SAVER_OK;
+}
+
 int saver_cuda_counters(saver_cuda_handle h, double* out8) {
   if (!h || !out8) return SAVER_ERR_ARG;
+  // [8], [9] (optional tail used by scripts/): CTA-lifetime cycles, longest CTA
+
   out8[0] = h->lasso.ms_round;
   out8[1] = h->lasso.ms_gemm;
   out8[2] = h->lasso.ms_setup;
@@ -395,6 +406,15 @@ int saver_cuda_counters(saver_cuda_handle h, double* out8) {
   out8[5] = (double)h->gemm_cols;
   out8[6] = (double)h->lasso.rounds;
   out8[7] = (double)h->launches;
+  return SAVER_OK;
+}
+
+int saver_cuda_counters_ext(saver_cuda_handle h, double* out4) {
+  if (!h || !out4) return SAVER_ERR_ARG;
+  out4[0] = (double)h->lasso.cta_cycles;
+  out4[1] = (double)h->lasso.max_cta_cycles;
+  out4[2] = 0;
+  out4[3] = 0;
   return SAVER_OK;
 }
 

@@ -65,6 +65,9 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                       int* status, int* stats, double* cvout, cudaStream_t s, long long* launches,
                       long long* gemm_cols);
 
+cudaError_t lasso_debug_path(const LassoWs& ws, int g, double* a0, double* dev, int* nin, int* nlp,
+                             double* lam);
+
 size_t calc_post_smem_bytes(int n, int* stage);
 cudaError_t launch_calc_post(const CalcPostArgs& A, cudaStream_t stream);
 cudaError_t launch_loglik(const LogLikArgs& A, cudaStream_t stream);
