@@ -155,6 +155,25 @@ SAVER_API int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, int
                                        double* est, double* se, double* info6, double* mu_out,
                                        int* status_out, int device_ptrs);
 
+/* ---- sample.saver (R/sample_saver.R:32-79) for a panel of B genes ----
+ * est, se: n x B.  nb_mode = 0: rgamma(shape = est^2/se^2, rate = est/se^2) rounded to 3
+ * decimals; 1 (efficiency.known): rnbinom(mu = est, size = est^2/se^2).  Counter-based generator:
+ * the draw for (gene, cell) depends only on (seed, rep_idx, gene0 + gene, cell), so any blocking or
+ * sharding of the genes gives the same dataset.  gene0 = index of the panel's first gene. */
+SAVER_API int saver_cuda_sample(saver_cuda_handle h, const double* est, const double* se, int n,
+                                int B, long long gene0, int nb_mode, unsigned long long seed,
+                                int rep_idx, double* out, int device_ptrs);
+
+/* ---- cor.genes / cor.cells (R/cor_adjust.R:26-66) ----
+ * est, se: n x G panels (one gene per column).  by_cells = 0: gene-gene (M = G vectors), 1:
+ * cell-cell (M = n).  out: M x ncols column block [col0, col0 + ncols) of
+ * cor(.) * outer(adj, adj), adj = sqrt(var / (var + mean(se^2))); col0 = 0, ncols = M for the
+ * whole matrix (ranks of a multi-GPU job take disjoint column blocks).  cor_in (optional): the
+ * same column block of a user-supplied cor.mat, used instead of computing the correlation. */
+SAVER_API int saver_cuda_cor_adjust(saver_cuda_handle h, const double* est, const double* se, int n,
+                                    int G, int by_cells, const double* cor_in, int col0, int ncols,
+                                    double* out, int device_ptrs);
+
 /* Problem columns pushed through the gradient GEMM so far (roofline accounting in bench.py):
  * every column is one 2 * n * p flop contraction against the resident design. */
 SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);

@@ -5,7 +5,8 @@ Host-side mirror of the reference's R function API over the C ABI of libsaver_cu
 sm_100a CUDA and raises if the library or a CUDA device is missing.
 """
 from . import host, ops  # noqa: F401
-from .host import SaverError, SaverResult, saver, saver_fit  # noqa: F401
+from .host import (SaverError, SaverResult, combine_saver, cor_cells, cor_genes, get_mu,  # noqa: F401
+                   sample_saver, saver, saver_fit, saver_fit_mean, saver_fit_null)
 from ._lib import Handle, SaverCudaError, default_handle  # noqa: F401
 
 __version__ = "0.1.0"

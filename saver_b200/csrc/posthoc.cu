@@ -1,0 +1,285 @@
+// posthoc.cu -- consumers of a fitted saver object: sample.saver and cor.genes / cor.cells.
+//
+// Replaces (reference file:line):
+//   R/sample_saver.R:32-79  rgamma(n, est^2/se^2, est/se^2) rounded to 3 decimals, or
+//                           rnbinom(n, mu = est, size = est^2/se^2)
+//   R/cor_adjust.R:26-66    cor(t(estimate)) (or cor(estimate)) * outer(adj, adj),
+//                           adj = sqrt(var / (var + mean(se^2)))
+// The reference draws from R's Mersenne-Twister with R's samplers; that stream is not
+// reproducible outside R, so parity for sampling is distributional (moments / KS tests).  The
+// generator here is counter-based (Philox4x32-10 keyed on the seed, counter = element index), so
+// a draw depends only on (seed, rep, gene, cell): results are identical however the genes are
+// blocked or sharded over GPUs.
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "ctx.h"
+
+using namespace saver;
+
+namespace {
+
+// ------------------------------------------------------------------ Philox4x32-10
+struct Philox {
+  uint32_t key[2];
+  uint32_t ctr[4];
+  uint32_t out[4];
+  int have;
+  __device__ Philox(uint64_t seed, uint64_t idx, uint32_t rep) {
+    key[0] = (uint32_t)seed;
+    key[1] = (uint32_t)(seed >> 32);
+    ctr[0] = (uint32_t)idx;
+    ctr[1] = (uint32_t)(idx >> 32);
+    ctr[2] = rep;
+    ctr[3] = 0;
+    have = 0;
+  }
+  __device__ void round10() {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+  __device__ uint32_t next32() {
+    if (have == 0) {
+      round10();
+      ctr[3] += 1;  // next block of this element's private stream
+      have = 4;
+    }
+    return out[4 - have--];
+  }
+  // uniform in (0, 1) with 53 random bits
+  __device__ double uniform() {
+    const uint64_t a = next32(), b = next32();
+    const uint64_t v = ((a << 32) | b) >> 11;
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  __device__ double normal() {  // Box-Muller, one value per call
+    const double u1 = uniform(), u2 = uniform();
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  }
+};
+
+// Marsaglia-Tsang gamma(shape, 1)
+__device__ double gamma_draw(Philox& g, double a) {
+  if (!(a > 0.0)) return a == 0.0 ? 0.0 : NAN;
+  double boost = 1.0;
+  if (a < 1.0) {
+    boost = pow(g.uniform(), 1.0 / a);
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int it = 0; it < 1000; ++it) {
+    const double x = g.normal();
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const double u = g.uniform();
+    if (u < 1.0 - 0.0331 * (x * x) * (x * x) || log(u) < 0.5 * x * x + d * (1.0 - v + log(v)))
+      return boost * d * v;
+  }
+  return boost * d;
+}
+
+// Poisson(lam): multiplication method for small means, Hoermann's PTRS otherwise
+__device__ double poisson_draw(Philox& g, double lam) {
+  if (!(lam >= 0.0)) return NAN;
+  if (lam == 0.0) return 0.0;
+  if (lam < 10.0) {
+    const double L = exp(-lam);
+    double p = 1.0;
+    int k = 0;
+    do {
+      ++k;
+      p *= g.uniform();
+    } while (p > L);
+    return (double)(k - 1);
+  }
+  const double slam = sqrt(lam), loglam = log(lam);
+  const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+  const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (int it = 0; it < 1000; ++it) {
+    const double u = g.uniform() - 0.5, v = g.uniform();
+    const double us = 0.5 - fabs(u);
+    const double k = floor((2.0 * a / us + b) * u + lam + 0.43);
+    if (us >= 0.07 && v <= vr) return k;
+    if (k < 0.0 || (us < 0.013 && v > us)) continue;
+    if (log(v) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0))
+      return k;
+  }
+  return floor(lam);
+}
+
+__global__ void sample_kernel(const double* __restrict__ est, const double* __restrict__ se,
+                              size_t total, size_t elem0, int nb_mode, uint64_t seed, uint32_t rep,
+                              double* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double e = est[i], s = se[i];
+    const double s2 = s * s;
+    const double shape = e * e / s2;  // NaN for the all-zero genes (0/0), as in R
+    Philox g(seed, elem0 + i, rep);
+    double v;
+    if (nb_mode) {
+      // rnbinom(mu, size): Poisson with a Gamma(size, scale = mu / size) mean
+      const double lam = gamma_draw(g, shape) * (e / shape);
+      v = poisson_draw(g, lam);
+    } else {
+      // rgamma(shape, rate = est / se^2), rounded to 3 decimals (R/sample_saver.R:57)
+      v = gamma_draw(g, shape) * (s2 / e);
+      v = rint(v * 1000.0) / 1000.0;
+    }
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ adjusted correlations
+// one CTA per vector (gene or cell): standardise to unit norm (so Z^T Z = cor) and compute adj
+__global__ void __launch_bounds__(256)
+cor_prep_kernel(const double* __restrict__ E, const double* __restrict__ S, int len, int ld_out,
+                double* __restrict__ Z, double* __restrict__ adj) {
+  __shared__ double scratch[16];
+  const int v = blockIdx.x;
+  const double* e = E + (size_t)v * len;
+  const double* s = S + (size_t)v * len;
+  double a[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < len; i += 256) {
+    a[0] += e[i];
+    a[1] += s[i] * s[i];
+  }
+  block_sum<2>(a, scratch);
+  double mean = a[0] / len, t = 0.0;
+  for (int i = threadIdx.x; i < len; i += 256) t += e[i] - mean;
+  mean += block_sum1(t, scratch) / len;
+  double ss = 0.0;
+  for (int i = threadIdx.x; i < len; i += 256) {
+    const double d = e[i] - mean;
+    ss += d * d;
+  }
+  ss = block_sum1(ss, scratch);
+  const double var = ss / (len - 1), mse = a[1] / len;
+  const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : NAN;  // constant vector: cor is NA in R
+  double* z = Z + (size_t)v * ld_out;
+  for (int i = threadIdx.x; i < ld_out; i += 256) z[i] = i < len ? (e[i] - mean) * inv : 0.0;
+  if (threadIdx.x == 0) adj[v] = sqrt(var / (var + mse));
+}
+
+__global__ void cor_scale_kernel(double* __restrict__ C, int ldc, int M, int ncols, int col0,
+                                 const double* __restrict__ adj, const double* __restrict__ cor_in,
+                                 int ld_in) {
+  const size_t tot = (size_t)M * ncols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % M), c = (int)(i / M);
+    const size_t o = (size_t)c * ldc + r;
+    double v = cor_in ? cor_in[(size_t)c * ld_in + r] : C[o];
+    if (!cor_in) v = fmin(1.0, fmax(-1.0, v));  // stats::cor clamps to [-1, 1]
+    C[o] = v * adj[r] * adj[col0 + c];
+  }
+}
+
+// (rows x cols, column-major, ld = rows) -> transpose
+__global__ void transpose_kernel(const double* __restrict__ in, int rows, int cols,
+                                 double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = bx + threadIdx.x, c = by + j;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)c * rows + r];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = by + threadIdx.x, r = bx + j;
+    if (r < rows && c < cols) out[(size_t)r * cols + c] = tile[threadIdx.x][j];
+  }
+}
+
+const int kGrid = 148 * 8;
+
+}  // namespace
+
+extern "C" int saver_cuda_sample(saver_cuda_handle h, const double* est, const double* se, int n, int B,
+                                 long long gene0, int nb_mode, unsigned long long seed, int rep_idx,
+                                 double* out, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!est || !se || !out || n < 1 || B < 0 || rep_idx < 0 || gene0 < 0)
+    return fail(h, SAVER_ERR_ARG, "sample: bad arguments");
+  if (B == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  const size_t nb = (size_t)n * B;
+  InArr<double> dE, dS;
+  OutArr<double> dO;
+  CU(dE.bind(est, nb, dev, s));
+  CU(dS.bind(se, nb, dev, s));
+  CU(dO.bind(out, nb, dev, s));
+  sample_kernel<<<kGrid, 256, 0, s>>>(dE.d, dS.d, nb, (size_t)gene0 * n, nb_mode, seed,
+                                     (uint32_t)rep_idx, dO.d);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(dO.fetch(s));
+  if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}
+
+extern "C" int saver_cuda_cor_adjust(saver_cuda_handle h, const double* est, const double* se, int n,
+                                     int G, int by_cells, const double* cor_in, int col0,
+                                     int ncols, double* out, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!est || !se || !out || n < 2 || G < 2) return fail(h, SAVER_ERR_ARG, "cor_adjust: bad arguments");
+  const int M = by_cells ? n : G;    // vectors being correlated
+  const int K = by_cells ? G : n;    // their length
+  if (col0 < 0 || ncols < 0 || col0 + ncols > M) return fail(h, SAVER_ERR_ARG, "cor_adjust: bad column block");
+  if (ncols == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  const size_t ng = (size_t)n * G;
+  InArr<double> dE, dS, dC;
+  OutArr<double> dO;
+  CU(dE.bind(est, ng, dev, s));
+  CU(dS.bind(se, ng, dev, s));
+  CU(dC.bind(cor_in, (size_t)M * ncols, dev, s));
+  CU(dO.bind(out, (size_t)M * ncols, dev, s));
+  const double *E = dE.d, *S = dS.d;
+  DevBuf<double> Et, St;
+  if (by_cells) {  // panels are gene-major (n x G); cells need genes contiguous: transpose
+    CU(Et.alloc(ng, s));
+    CU(St.alloc(ng, s));
+    dim3 tg((n + 31) / 32, (G + 31) / 32), tb(32, 8);
+    transpose_kernel<<<tg, tb, 0, s>>>(dE.d, n, G, Et.p);
+    transpose_kernel<<<tg, tb, 0, s>>>(dS.d, n, G, St.p);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    E = Et.p;
+    S = St.p;
+  }
+  const int ldk = (K + 15) / 16 * 16, M_pad = (M + 127) / 128 * 128;
+  DevBuf<double> Z, adj;
+  const int Zcols = M_pad + 64;  // the GEMM reads up to round_up(ncols, 64) columns past col0
+  CU(Z.alloc((size_t)ldk * Zcols, s));
+  CU(adj.alloc(M_pad, s));
+  CU(cudaMemsetAsync(Z.p + (size_t)ldk * M, 0, (size_t)ldk * (Zcols - M) * 8, s));
+  cor_prep_kernel<<<M, 256, 0, s>>>(E, S, K, ldk, Z.p, adj.p);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  if (!dC.d) {
+    CU(launch_gemm_tn_f64(Z.p, ldk, Z.p + (size_t)ldk * col0, ldk, dO.d, M, M, ncols, ldk, s));
+    h->launches += 1;
+  }
+  cor_scale_kernel<<<kGrid, 256, 0, s>>>(dO.d, M, M, ncols, col0, adj.p, dC.d, M);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(dO.fetch(s));
+  if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}

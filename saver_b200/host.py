@@ -513,3 +513,59 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
     if estimates_only and not return_mu:
         return res.estimate
     return res
+
+
+# ----------------------------------------------------------------------------------------------
+# consumers of a saver object
+# ----------------------------------------------------------------------------------------------
+def sample_saver(x, rep=1, efficiency_known=False, seed=None, handle=None, block=4096):
+    """sample.saver (R/sample_saver.R:32-79).  x: SaverResult.  Returns one (G, n) array, or a
+    list of ``rep`` arrays.  seed=None draws a fresh seed (R: the ambient RNG state)."""
+    rep = int(rep)
+    if rep <= 0:
+        raise SaverError("rep must be a positive integer.")
+    if seed is None:
+        seed = int(np.random.SeedSequence().generate_state(1)[0])
+    est, se = np.asarray(x.estimate), np.asarray(x.se)
+    outs = []
+    for j in range(rep):
+        out = np.empty_like(est)
+        for b0 in range(0, est.shape[0], block):
+            sl = slice(b0, b0 + block)
+            out[sl] = ops.sample(est[sl], se[sl], nb_mode=efficiency_known, seed=seed, rep_idx=j,
+                                 gene0=b0, handle=handle)
+        outs.append(out)
+    return outs[0] if rep == 1 else outs
+
+
+def cor_genes(x, cor_mat=None, handle=None):
+    """cor.genes (R/cor_adjust.R:26-44): gene-gene correlation of the estimates, shrunk by the
+    posterior uncertainty.  The diagonal is adj^2, not 1, exactly as in the reference."""
+    return ops.cor_adjust(np.asarray(x.estimate), np.asarray(x.se), by_cells=False, cor_in=cor_mat,
+                          handle=handle)
+
+
+def cor_cells(x, cor_mat=None, handle=None):
+    """cor.cells (R/cor_adjust.R:48-66)."""
+    return ops.cor_adjust(np.asarray(x.estimate), np.asarray(x.se), by_cells=True, cor_in=cor_mat,
+                          handle=handle)
+
+
+def get_mu(x, saver_obj):
+    """get.mu (R/get_mu.R:22-25): the prior mean behind a saver object (host arithmetic)."""
+    est, se = np.asarray(saver_obj.estimate), np.asarray(saver_obj.se)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mu = (est ** 2 / se ** 2 - np.asarray(x)) / (est / se ** 2 - saver_obj.info["size.factor"])
+    return np.round(mu, 3)
+
+
+def combine_saver(saver_list):
+    """combine.saver (R/combine_saver.R:25-44): stack objects fitted on gene subsets."""
+    est = np.concatenate([s.estimate for s in saver_list], 0)
+    se = np.concatenate([s.se for s in saver_list], 0)
+    info = {"size.factor": saver_list[0].info["size.factor"]}
+    for k in ("maxcor", "lambda.max", "lambda.min", "sd.cv", "pred.time", "var.time", "cutoff",
+              "lambda.coefs"):
+        info[k] = np.concatenate([np.atleast_1d(s.info[k]) for s in saver_list])
+    info["total.time"] = float(sum(s.info["total.time"] for s in saver_list))
+    return SaverResult(est, se, info)

@@ -236,3 +236,40 @@ def calc_estimate(x, sf, scale_sf, mode, cutoff=0.0, coefs=None, self_col=None, 
         ptr(info), ptr(mu), ptr(status), int(dev)))
     return dict(est=est, se=se, maxcor=info[0], lambda_max=info[1], lambda_min=info[2],
                 sd_cv=info[3], ct=info[4], vt=info[5], status=status, mu=mu)
+
+
+def sample(est, se, nb_mode=False, seed=0, rep_idx=0, gene0=0, handle=None):
+    """sample.saver draws for a panel: est, se (B, n) -> (B, n)."""
+    h = handle or default_handle()
+    dev = is_device(est)
+    if dev:
+        import torch
+        out = torch.empty_like(est)
+    else:
+        est, se = _f64(np.atleast_2d(est)), _f64(np.atleast_2d(se))
+        out = np.empty_like(est)
+    B, n = est.shape
+    h.check(h.lib.saver_cuda_sample(h.h, ptr(est), ptr(se), n, B, C.c_longlong(int(gene0)),
+                                    int(bool(nb_mode)), C.c_ulonglong(int(seed) & (2**64 - 1)),
+                                    int(rep_idx), ptr(out), int(dev)))
+    return out
+
+
+def cor_adjust(est, se, by_cells=False, cor_in=None, col0=0, ncols=None, handle=None):
+    """cor.genes / cor.cells: est, se (G, n) -> (ncols, M) rows = the requested columns of the
+    symmetric adjusted correlation (M = G, or n when by_cells)."""
+    h = handle or default_handle()
+    dev = is_device(est)
+    G, n = est.shape
+    M = n if by_cells else G
+    ncols = M - col0 if ncols is None else ncols
+    if dev:
+        import torch
+        out = torch.empty((ncols, M), dtype=torch.float64, device=est.device)
+    else:
+        est, se = _f64(est), _f64(se)
+        cor_in = None if cor_in is None else _f64(cor_in)
+        out = np.empty((ncols, M))
+    h.check(h.lib.saver_cuda_cor_adjust(h.h, ptr(est), ptr(se), n, G, int(bool(by_cells)),
+                                        ptr(cor_in), int(col0), int(ncols), ptr(out), int(dev)))
+    return out
