@@ -181,7 +181,7 @@ __global__ void cor_scale_kernel(double* __restrict__ C, int ldc, int M, int nco
     const int r = (int)(i % M), c = (int)(i / M);
     const size_t o = (size_t)c * ldc + r;
     double v = cor_in ? cor_in[(size_t)c * ld_in + r] : C[o];
-    if (!cor_in) v = fmin(1.0, fmax(-1.0, v));  // stats::cor clamps to [-1, 1]
+    if (!cor_in && v == v) v = fmin(1.0, fmax(-1.0, v));  // stats::cor clamps to [-1, 1]; NA stays NA
     C[o] = v * adj[r] * adj[col0 + c];
   }
 }
