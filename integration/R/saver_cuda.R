@@ -1,0 +1,89 @@
+# saver_cuda.R -- the R side of the drop-in: the bodies a maintainer of mohuangx/SAVER swaps in.
+# Signatures are the reference's (NAMESPACE:3-23); everything numerical is one .Call into
+# libsaver_cuda (src/rcall_shim.c).  Untested here: the build image has no R (DESIGN.md 1b).
+
+.saver.cuda <- new.env()
+saver.cuda.handle <- function() {
+  if (is.null(.saver.cuda$h))
+    .saver.cuda$h <- .Call(C_saver_cuda_create, as.integer(getOption("saver.cuda.device", 0L)))
+  .saver.cuda$h
+}
+
+# cv.glmnet's fold draw, done by the host so folds are identical to the reference's
+# (R/expr_predict.R:35-36: set.seed(seed); cv.glmnet then calls sample(rep(seq(nfolds), length = N)))
+.draw.folds <- function(seeds, pred.cells, ncells, nfolds = 5L) {
+  fold <- matrix(0L, ncells, length(seeds))
+  for (i in seq_along(seeds)) {
+    set.seed(seeds[i])
+    fold[pred.cells, i] <- sample(rep(seq(nfolds), length = length(pred.cells)))
+  }
+  fold
+}
+
+# replaces R/calc_estimate.R:65-161 (same arguments, same 8-element result)
+calc.estimate <- function(x, x.est, cutoff = 0, coefs = NULL, sf, scale.sf, pred.gene.names,
+                          pred.cells, null.model, nworkers, calc.maxcor, estimates.only) {
+  h <- saver.cuda.handle()
+  x <- as.matrix(x)
+  if (!identical(.saver.cuda$design, x.est)) {      # x.est is installed once per saver() call
+    .Call(C_saver_cuda_set_design, h, x.est)
+    .saver.cuda$design <- x.est
+  }
+  ncells <- ncol(x)
+  self.col <- match(rownames(x), colnames(x.est), nomatch = 0L) - 1L   # 0-based, -1 = none
+  is.pred <- as.integer(rownames(x) %in% pred.gene.names)
+  mask <- integer(ncells); mask[pred.cells] <- 1L
+  mode <- if (null.model) 0L else if (is.null(coefs)) 1L else 2L
+  foldid <- if (mode == 1L) .draw.folds(seq_len(nrow(x)), pred.cells, ncells) else NULL
+  out <- .Call(C_saver_cuda_calc_estimate, h, t(x), as.numeric(sf), as.numeric(scale.sf),
+               as.integer(self.col), is.pred, mask, foldid, mode, as.logical(calc.maxcor),
+               as.numeric(cutoff), if (is.null(coefs)) NULL else as.numeric(coefs),
+               as.logical(estimates.only))
+  info <- out[[3]]
+  list(est = t(out[[1]]), se = if (estimates.only) NA else t(out[[2]]), maxcor = info[, 1],
+       lambda.max = info[, 2], lambda.min = info[, 3], sd.cv = info[, 4], ct = info[, 5],
+       vt = info[, 6])
+}
+
+# replaces R/calc_posterior.R:26-68, R/optimize_variance.R:24-134, R/calc_loglik.R:26-75
+calc.post <- function(y, mu, sf, scale.sf) {
+  out <- .Call(C_saver_cuda_calc_post, saver.cuda.handle(), as.numeric(y), as.numeric(mu),
+               rep_len(as.numeric(sf), length(y)), as.numeric(scale.sf))
+  list(estimate = out[[1]], se = out[[2]])
+}
+calc.a <- function(y, mu, sf) .Call(C_saver_cuda_calc_var, saver.cuda.handle(), 0L, as.numeric(y), as.numeric(mu), as.numeric(sf))
+calc.b <- function(y, mu, sf) .Call(C_saver_cuda_calc_var, saver.cuda.handle(), 1L, as.numeric(y), as.numeric(mu), as.numeric(sf))
+calc.k <- function(y, mu, sf) .Call(C_saver_cuda_calc_var, saver.cuda.handle(), 2L, as.numeric(y), as.numeric(mu), as.numeric(sf))
+calc.loglik.a <- function(a, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.handle(), 0L, a, as.numeric(y), as.numeric(mu), as.numeric(sf))
+calc.loglik.b <- function(b, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.handle(), 1L, b, as.numeric(y), as.numeric(mu), as.numeric(sf))
+calc.loglik.k <- function(k, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.handle(), 2L, k, as.numeric(y), as.numeric(mu), as.numeric(sf))
+
+# replaces R/calc_maxcor.R:26-42
+calc.maxcor <- function(x1, x2) {
+  h <- saver.cuda.handle()
+  .Call(C_saver_cuda_set_design, h, x1)
+  self.col <- match(colnames(x2), colnames(x1), nomatch = 0L) - 1L
+  .Call(C_saver_cuda_maxcor, h, x2, as.integer(self.col))
+}
+
+# replaces R/sample_saver.R:32-79 and R/cor_adjust.R:26-66
+sample.saver <- function(x, rep = 1, efficiency.known = FALSE, seed = NULL) {
+  rep <- as.integer(rep)
+  if (rep <= 0) stop("rep must be a positive integer.")
+  if (is.null(seed)) seed <- sample.int(.Machine$integer.max, 1)
+  draw <- function(j) {
+    s <- t(.Call(C_saver_cuda_sample, saver.cuda.handle(), t(x$estimate), t(x$se),
+                 as.logical(efficiency.known), as.numeric(seed), as.integer(j - 1L)))
+    dimnames(s) <- dimnames(x$estimate)
+    s
+  }
+  if (rep == 1) draw(1L) else lapply(seq_len(rep), draw)
+}
+cor.genes <- function(x, cor.mat = NULL)
+  .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(x$se), FALSE, cor.mat)
+cor.cells <- function(x, cor.mat = NULL)
+  .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(x$se), TRUE, cor.mat)
+
+# saver(), saver.fit(), saver.fit.mean/.null, get.mu, combine.saver and R/utils.R stay as they are
+# in the reference (they only call the functions above); saver() forces ncores to one process:
+#   if (ncores > 1) message("libsaver_cuda: device parallelism replaces ", ncores, " PSOCK workers")

@@ -1,0 +1,166 @@
+/*
+ * rcall_shim.c -- .Call glue between R and libsaver_cuda (include/saver_cuda.h).
+ *
+ * Compiled only where R exists (R CMD SHLIB, needs Rinternals.h); it cannot be built in the
+ * image this repo is developed in (no R).  Pure marshalling: every numerical decision lives behind
+ * the header-free C ABI.  R matrices are column-major; a block of genes travels as t(x[block, ])
+ * (n x B, one gene per column), which is the panel layout of the ABI.
+ * Never longjmp (Rf_error) across a live CUDA frame: errors are turned into R conditions only
+ * after the library call has returned.
+ */
+#include <R.h>
+#include <Rinternals.h>
+
+#include "saver_cuda.h"
+
+static void handle_finalizer(SEXP ptr)
+{
+    saver_cuda_handle h = (saver_cuda_handle)R_ExternalPtrAddr(ptr);
+    if (h) saver_cuda_destroy(h);
+    R_ClearExternalPtr(ptr);
+}
+
+static saver_cuda_handle get_handle(SEXP ptr)
+{
+    saver_cuda_handle h = (saver_cuda_handle)R_ExternalPtrAddr(ptr);
+    if (!h) Rf_error("libsaver_cuda handle is closed");
+    return h;
+}
+
+static void check(saver_cuda_handle h, int rc)
+{
+    if (rc != SAVER_OK) Rf_error("libsaver_cuda error %d: %s", rc, saver_cuda_last_error(h));
+}
+
+SEXP C_saver_cuda_create(SEXP device)
+{
+    saver_cuda_handle h = NULL;
+    int rc = saver_cuda_create(Rf_asInteger(device), &h);
+    if (rc != SAVER_OK) Rf_error("no usable CUDA device (libsaver_cuda has no CPU fallback), code %d", rc);
+    SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* x.est: n x p numeric matrix (R/saver.R:157) */
+SEXP C_saver_cuda_set_design(SEXP hp, SEXP xest)
+{
+    saver_cuda_handle h = get_handle(hp);
+    check(h, saver_cuda_set_design(h, REAL(xest), Rf_nrows(xest), Rf_ncols(xest), 0));
+    return R_NilValue;
+}
+
+/* the foreach body of calc.estimate (R/calc_estimate.R:75-141) for one block.
+ * xt: n x B = t(x[block, ]); foldid: n x B integer or NULL; returns the 8-element list. */
+SEXP C_saver_cuda_calc_estimate(SEXP hp, SEXP xt, SEXP sf, SEXP scale_sf, SEXP self_col,
+                                SEXP is_pred, SEXP pred_mask, SEXP foldid, SEXP mode,
+                                SEXP calc_maxcor, SEXP cutoff, SEXP coefs, SEXP estimates_only)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_nrows(xt), B = Rf_ncols(xt), eo = Rf_asLogical(estimates_only);
+    SEXP est = PROTECT(Rf_allocMatrix(REALSXP, n, B));
+    SEXP se = PROTECT(eo ? Rf_ScalarLogical(NA_LOGICAL) : Rf_allocMatrix(REALSXP, n, B));
+    SEXP info = PROTECT(Rf_allocMatrix(REALSXP, B, 6));
+    int rc = saver_cuda_calc_estimate(
+        h, REAL(xt), n, B, REAL(sf), Rf_asReal(scale_sf), INTEGER(self_col), INTEGER(is_pred),
+        Rf_isNull(pred_mask) ? NULL : INTEGER(pred_mask), Rf_isNull(foldid) ? NULL : INTEGER(foldid),
+        5, Rf_asInteger(mode), Rf_asLogical(calc_maxcor), Rf_asReal(cutoff),
+        Rf_isNull(coefs) ? NULL : REAL(coefs), 300, 100, 1e-7, REAL(est), eo ? NULL : REAL(se),
+        REAL(info), NULL, NULL, 0);
+    check(h, rc);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, est);   /* n x B: the R wrapper transposes into B x n */
+    SET_VECTOR_ELT(out, 1, se);
+    SET_VECTOR_ELT(out, 2, info);  /* columns: maxcor, lambda.max, lambda.min, sd.cv, ct, vt */
+    UNPROTECT(4);
+    return out;
+}
+
+/* calc.post(y, mu, sf, scale.sf) for one gene (R/calc_posterior.R:26) */
+SEXP C_saver_cuda_calc_post(SEXP hp, SEXP y, SEXP mu, SEXP sf, SEXP scale_sf)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_length(y);
+    SEXP est = PROTECT(Rf_allocVector(REALSXP, n)), se = PROTECT(Rf_allocVector(REALSXP, n));
+    check(h, saver_cuda_calc_post(h, REAL(y), REAL(mu), Rf_length(mu) == 1, REAL(sf), n, 1,
+                                  Rf_asReal(scale_sf), REAL(est), REAL(se), NULL, NULL, NULL, NULL, 0));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, est);
+    SET_VECTOR_ELT(out, 1, se);
+    UNPROTECT(3);
+    return out;
+}
+
+/* calc.a / calc.b / calc.k and calc.loglik.* (R/optimize_variance.R, R/calc_loglik.R) */
+SEXP C_saver_cuda_calc_var(SEXP hp, SEXP model, SEXP y, SEXP mu, SEXP sf)
+{
+    saver_cuda_handle h = get_handle(hp);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
+    int flags = 0;
+    check(h, saver_cuda_calc_var(h, Rf_asInteger(model), REAL(y), REAL(mu), Rf_length(mu), REAL(sf),
+                                 Rf_length(sf), Rf_length(y), REAL(out), &flags, NULL));
+    UNPROTECT(1);
+    return out;
+}
+
+SEXP C_saver_cuda_loglik(SEXP hp, SEXP model, SEXP param, SEXP y, SEXP mu, SEXP sf)
+{
+    saver_cuda_handle h = get_handle(hp);
+    double v = 0;
+    check(h, saver_cuda_loglik(h, Rf_asInteger(model), Rf_asReal(param), REAL(y), REAL(mu),
+                               Rf_length(mu), REAL(sf), Rf_length(sf), Rf_length(y), &v));
+    return Rf_ScalarReal(v);
+}
+
+/* calc.maxcor(x.est, t(y)) with the design already installed */
+SEXP C_saver_cuda_maxcor(SEXP hp, SEXP yt, SEXP self_col)
+{
+    saver_cuda_handle h = get_handle(hp);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_ncols(yt)));
+    check(h, saver_cuda_maxcor(h, REAL(yt), Rf_ncols(yt), INTEGER(self_col), REAL(out), 0));
+    UNPROTECT(1);
+    return out;
+}
+
+/* sample.saver / cor.genes / cor.cells on t(estimate), t(se) (n x G) */
+SEXP C_saver_cuda_sample(SEXP hp, SEXP est_t, SEXP se_t, SEXP nb, SEXP seed, SEXP rep)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_nrows(est_t), G = Rf_ncols(est_t);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, G));
+    check(h, saver_cuda_sample(h, REAL(est_t), REAL(se_t), n, G, 0, Rf_asLogical(nb),
+                               (unsigned long long)Rf_asReal(seed), Rf_asInteger(rep), REAL(out), 0));
+    UNPROTECT(1);
+    return out;
+}
+
+SEXP C_saver_cuda_cor_adjust(SEXP hp, SEXP est_t, SEXP se_t, SEXP by_cells, SEXP cor_mat)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_nrows(est_t), G = Rf_ncols(est_t), bc = Rf_asLogical(by_cells);
+    const int M = bc ? n : G;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, M, M));
+    check(h, saver_cuda_cor_adjust(h, REAL(est_t), REAL(se_t), n, G, bc,
+                                   Rf_isNull(cor_mat) ? NULL : REAL(cor_mat), 0, M, REAL(out), 0));
+    UNPROTECT(1);
+    return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"C_saver_cuda_create", (DL_FUNC)&C_saver_cuda_create, 1},
+    {"C_saver_cuda_set_design", (DL_FUNC)&C_saver_cuda_set_design, 2},
+    {"C_saver_cuda_calc_estimate", (DL_FUNC)&C_saver_cuda_calc_estimate, 13},
+    {"C_saver_cuda_calc_post", (DL_FUNC)&C_saver_cuda_calc_post, 5},
+    {"C_saver_cuda_calc_var", (DL_FUNC)&C_saver_cuda_calc_var, 5},
+    {"C_saver_cuda_loglik", (DL_FUNC)&C_saver_cuda_loglik, 6},
+    {"C_saver_cuda_maxcor", (DL_FUNC)&C_saver_cuda_maxcor, 3},
+    {"C_saver_cuda_sample", (DL_FUNC)&C_saver_cuda_sample, 6},
+    {"C_saver_cuda_cor_adjust", (DL_FUNC)&C_saver_cuda_cor_adjust, 5},
+    {NULL, NULL, 0}};
+
+void R_init_SAVERcuda(DllInfo* dll)
+{
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
