@@ -185,6 +185,16 @@ SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);
 SAVER_API int saver_cuda_counters(saver_cuda_handle h, double* out8);
 /* [0] sum of round-kernel CTA lifetimes (SM cycles), [1] the longest single CTA; [2..3] reserved */
 SAVER_API int saver_cuda_counters_ext(saver_cuda_handle h, double* out4);
+/* Summed SM cycles of the Gram round kernel per phase: [0] gradient/KKT/strong rule, [1] gradient
+ * vectors, [2] Gram block (DMMA), [3] Gram-space sweeps, [4] residual materialisation, [5] strong-set
+ * check, [6] re-linearisation, [7] number of IRLS steps, [8] Gram-space coordinate steps, [9] sweeps,
+ * [10] strong-set columns checked, [11] checks, [12] sum of |A| over IRLS steps; out has 16 slots. */
+SAVER_API int saver_cuda_phase_cycles(saver_cuda_handle h, double* out16);
+
+/* Solver options.  "lasso_gram" (default 1): 1 = Gram-space round kernel; 0 = the n-space kernel
+ * that follows glmnet's fishnet1 sweep for sweep (slower; agrees with the CPU oracle to rounding on
+ * most genes).  "strong_slack" (default 1 = sequential strong rule).  "lasso_dbg": bring-up bits. */
+SAVER_API int saver_cuda_set_option(saver_cuda_handle h, const char* key, double value);
 
 /* Diagnostics: the master path of gene g of the LAST block the solver ran -- per lambda (128
  * slots) intercept, deviance ratio, ever-active count, cumulative sweeps, lambda. */

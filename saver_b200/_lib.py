@@ -80,6 +80,9 @@ class Handle:
         self.check(self.lib.saver_cuda_stream(self.h, C.byref(s)))
         return s.value or 0
 
+    def set_option(self, key, value):
+        self.check(self.lib.saver_cuda_set_option(self.h, key.encode(), C.c_double(float(value))))
+
     def launch_count(self):
         return int(self.lib.saver_cuda_launch_count(self.h))
 

@@ -13,7 +13,10 @@ struct saver_cuda_ctx {
   cudaStream_t stream = nullptr;
   long long launches = 0;
   long long gemm_cols = 0;  // problem columns pushed through the gradient GEMM (lasso rounds)
-  double ms_post = 0, ms_maxcor = 0;  // device time of the variance/posterior and maxcor phases
+  double ms_post = 0, ms_maxcor = 0;
+  int opt_gram = 1;            // saver_cuda_set_option("lasso_gram")
+  double opt_strong_slack = 1.0;
+  int opt_dbg = 0;  // device time of the variance/posterior and maxcor phases
   char err[512] = {0};
   saver::DesignState design;
   saver::LassoWs lasso;

@@ -63,12 +63,12 @@ struct RoundArgs {
 // ---------------------------------------------------------------------------------------------
 // block reductions: every thread receives bit-identical totals (butterfly sums commute), so all
 // scalar control flow below is uniform across the CTA without broadcasts.  One __syncthreads per
-// call; `buf` holds 2 x 4 x 32 doubles and alternates so back-to-back calls do not race.
+// call; `buf` holds 2 x 8 x 32 doubles and alternates so back-to-back calls do not race.
 // ---------------------------------------------------------------------------------------------
 template <int K>
 __device__ __forceinline__ void bsum(double (&v)[K], double* buf, int& phase) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double* b = buf + phase * 128;
+  double* b = buf + phase * 256;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     v[k] = warp_sum(v[k]);
@@ -87,7 +87,7 @@ __device__ __forceinline__ void bsum(double (&v)[K], double* buf, int& phase) {
 
 __device__ __forceinline__ double bmax(double v, double* buf, int& phase) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double* b = buf + phase * 128;
+  double* b = buf + phase * 256;
   v = warp_max(v);
   if (lane == 0) b[warp] = v;
   __syncthreads();
@@ -108,6 +108,12 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
@@ -117,7 +123,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
 // null-model constants of fishnet1.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lasso_setup_kernel(RoundArgs A) {
-  __shared__ double red[256];
+  __shared__ double red[512];
   int phase = 0;
   const int pid = blockIdx.x, tid = threadIdx.x;
   const int NF = A.prm.NF, g = pid / NF, fit = pid % NF, n = A.n;
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(256) lasso_moments_kernel(RoundArgs A) {
 
 // null-model working weights / residual (fishnet1 prologue) -> W, WR and the GEMM panel R
 __global__ void __launch_bounds__(256) lasso_resid0_kernel(RoundArgs A) {
-  __shared__ double red[256];
+  __shared__ double red[512];
   int phase = 0;
   const int pid = blockIdx.x, tid = threadIdx.x, n = A.n, ldx = A.ldx;
   LassoProb* PR = A.ws.prob + pid;
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(256) lasso_resid0_kernel(RoundArgs A) {
 // values as a user sequence (cv.glmnet passes lambda = master$lambda, whose first entry has been
 // replaced by exp(2 log l2 - log l3), glmnet's fix.lam).
 __global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
-  __shared__ double red[256];
+  __shared__ double red[512];
   int phase = 0;
   const int g = blockIdx.x, tid = threadIdx.x, pid = g * A.prm.NF;
   const LassoProb* PR = A.ws.prob + pid;
@@ -285,7 +291,9 @@ __global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
 // the round kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kMeta = 64;  // strong-set metadata staged per chunk
-constexpr int kFixedSmem = 256 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4 + kMeta * (8 + 8 + 4 + 4) + 16;
+constexpr int kHSlots = 148 * 4;  // Gram scratch slots (>= resident CTAs of the gram kernel)
+constexpr int kGramSmem = 3 * kNX * 8 + 64 + kNX * 4;  // gq, gq2, amat, gsh, ord
+constexpr int kFixedSmem = 512 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4 + kMeta * (8 + 8 + 4 + 4) + 16;
 
 template <int T>
 __device__ __forceinline__ int rebuild_strong(const int* MMc, int* SIc, int p, int* ish) {
@@ -319,7 +327,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
                    int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* red = reinterpret_cast<double*>(smraw);
-  double* aact = red + 256;
+  double* aact = red + 512;
   double* as_ = aact + kNX;
   double* va = as_ + kNX;
   double* swa = va + kNX;
@@ -791,6 +799,922 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   }
 }
 
+// One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane), the
+// Hessian column of step t+NB-1 is requested while step t runs, the reciprocal of the curvature
+// is formed off the critical path.  Results (dlx, q0, changed flag) go through `gsh`.
+template <int Q, int NB>
+__device__ __noinline__ void gram_sweep_warp(const double* H, int ldh, int m, bool by_index,
+                                             const int* ord, double* gq, const double* va,
+                                             double* aact, const double* swa, double al,
+                                             double* gsh, double dlx, double q0) {
+  const int lane = threadIdx.x & 31;
+  double qr[Q], hb[NB][Q];
+#pragma unroll
+  for (int e = 0; e < Q; ++e) {
+    const int j = lane + 32 * e;
+    qr[e] = j < m ? gq[j] : 0.0;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (b < m) {
+      const int l = by_index ? ord[b] : b;
+#pragma unroll
+      for (int e = 0; e < Q; ++e) {
+        const int j = lane + 32 * e;
+        hb[b][e] = j < m ? H[j + (size_t)l * ldh] : 0.0;
+      }
+    }
+  }
+  bool dty = false, bad = false;
+  int ln = by_index ? ord[0] : 0;
+  double vn = va[ln], an = aact[ln], sn = swa[ln];
+  double rn = 1.0 / vn;
+  for (int t0 = 0; t0 < m && !bad; t0 += NB) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int t = t0 + b;
+      if (t < m && !bad) {
+        const int l = ln;
+        const double v = vn, ak = an, sw = sn, rv = rn;
+        if (t + 1 < m) {
+          ln = by_index ? ord[t + 1] : t + 1;
+          vn = va[ln]; an = aact[ln]; sn = swa[ln];
+          rn = 1.0 / vn;
+        }
+        double sel = qr[0];
+        const int qi = l >> 5;
+#pragma unroll
+        for (int e = 1; e < Q; ++e) sel = qi == e ? qr[e] : sel;
+        const double ql = __shfl_sync(0xffffffffu, sel, l & 31);
+        const double u = ql + v * ak;
+        const double au = fabs(u) - al;
+        // glmnet: sign(au, u) / v ; the reciprocal differs from the division by <= 1 ulp
+        const double anew = au > 0.0 ? (u > 0.0 ? au : -au) * rv : 0.0;
+        if (anew != ak) {
+          if (anew != anew) {
+            bad = true;
+          } else {
+            const double d = anew - ak;
+            dlx = fmax(dlx, v * d * d);
+#pragma unroll
+            for (int e = 0; e < Q; ++e) qr[e] -= d * hb[b][e];
+            q0 -= d * sw;
+            if (lane == 0) aact[l] = anew;
+            dty = true;
+          }
+        }
+        if (t + NB < m) {
+          const int l2 = by_index ? ord[t + NB] : t + NB;
+#pragma unroll
+          for (int e = 0; e < Q; ++e) {
+            const int j = lane + 32 * e;
+            hb[b][e] = j < m ? H[j + (size_t)l2 * ldh] : 0.0;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < Q; ++e) {
+    const int j = lane + 32 * e;
+    if (j < m) gq[j] = qr[e];
+  }
+  if (lane == 0) {
+    gsh[0] = bad ? NAN : dlx;
+    gsh[1] = q0;
+    gsh[2] = dty ? 1.0 : 0.0;
+  }
+}
+
+// The Gram-space round kernel (default): same state machine and phase A as lasso_round_kernel,
+// phase B reformulated so that no coordinate update touches an n-long vector.
+template <int T, bool STAGED>
+__global__ void __launch_bounds__(T, (T <= 256 ? 2 : 1))
+lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ nextlist,
+                   int* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* red = reinterpret_cast<double*>(smraw);
+  double* aact = red + 512;
+  double* as_ = aact + kNX;
+  double* va = as_ + kNX;
+  double* swa = va + kNX;
+  double* xma = swa + kNX;
+  double* xia = xma + kNX;
+  int* ia = reinterpret_cast<int*>(xia + kNX);
+  int* ish = ia + kNX;
+  double* mxm = reinterpret_cast<double*>(ish + 64);   // staged strong-set metadata
+  double* mxi = mxm + kMeta;
+  int* mk = reinterpret_cast<int*>(mxi + kMeta);
+  int* mpos = mk + kMeta + 4;  // mk has one extra slot: first column of the next chunk
+  double* gq = reinterpret_cast<double*>(mpos + kMeta);  // gradient on the active set
+  double* gq2 = gq + kNX;                                  // second buffer of the gradient
+  double* amat = gq2 + kNX;                                // coefficients at the last materialisation
+  double* gsh = amat + kNX;                                // 8 doubles: sweep results broadcast from warp 0
+  int* ord = reinterpret_cast<int*>(gsh + 8);              // active positions by variable index
+  double* wv = reinterpret_cast<double*>(ord + kNX);
+  double* wrv = wv + A.ldx;
+
+  const int tid = threadIdx.x;
+  int phase = 0;
+  unsigned ncols = 0;  // design columns this CTA streamed (roofline accounting)
+  unsigned long long gram_fma = 0;  // FP64 FMAs issued on DMMA for Gram blocks
+  long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // cycles: phaseA, vectors, gramP, sweeps, materialise, inactive, relin, irls count; [8] sweep steps [9] sweeps [10] inactive columns [11] checks [12] sum m at Gram build
+  long long tmark = clock64();
+  const bool timing = (A.prm.dbg & 128) != 0;
+  auto lap = [&](int k) {
+    if (timing) { const long long t = clock64(); tph[k] += t - tmark; tmark = t; }
+  };
+  int ninact = 0;
+  int* INc = A.ws.INACT + (size_t)list[blockIdx.x] * A.p_pad;
+  const long long t_start = clock64();
+  const int pid = list[blockIdx.x];
+  LassoProb* PR = A.ws.prob + pid;
+  const int g = PR->gene, fit = PR->fit, slot = PR->slot;
+  int state = PR->state, lidx = PR->lidx, lmu = PR->lmu, nin = PR->nin, nS = PR->nS;
+  int jerr = PR->jerr, nlp = PR->nlp;
+  double al = PR->al, al0 = PR->al0, az = PR->az, v0 = PR->v0, sumr = PR->sumr;
+  double cur_dev = PR->cur_dev, cur_cv = PR->cur_cv;
+  const double qv = PR->qv, dv0 = PR->dv0, dvr = PR->dvr, shr = PR->shr, ncv = PR->ncv;
+  const int n = A.n, ldx = A.ldx, p = A.p, p_pad = A.p_pad;
+  const double* __restrict__ Xs = A.Xs;
+  const double* Gc = A.ws.G + (size_t)slot * p_pad;
+  const double* XMc = A.ws.XM + (size_t)pid * p_pad;
+  const double* XIc = A.ws.XI + (size_t)pid * p_pad;
+  int* MMc = A.ws.MM + (size_t)pid * p_pad;
+  int* SIc = A.ws.SIDX + (size_t)pid * p_pad;
+  int* IAg = A.ws.IA + (size_t)pid * kNX;
+  double* AAg = A.ws.AACT + (size_t)pid * kNX;
+  double* Wg = A.ws.W + (size_t)pid * ldx;
+  double* WRg = A.ws.WR + (size_t)pid * ldx;
+  const double* y = A.Yn + (size_t)g * n;
+  const int* fo = A.fold + (size_t)g * n;
+  const int self = A.self ? A.self[g] : -1;
+  const int nvars = p - (self >= 0 ? 1 : 0);
+  int nx = 2 * A.prm.dfmax + 20;
+  if (nx > nvars) nx = nvars;
+  if (nx > kNX) nx = kNX;
+  const int ne = A.prm.dfmax;
+  const int nlam = A.ws.nlam_g[g];
+  const double* lamg = A.ws.lam + (size_t)g * kNLam;
+  const bool master_auto = A.prm.auto_lambda && fit == 0;
+  const bool is_fold = fit > 0;
+  const int maxit = A.prm.maxit;
+  const double fmax_ = log(DBL_MAX * 0.1);
+
+  if (!STAGED) {
+    wv = Wg;
+    wrv = WRg;
+  } else {
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      *reinterpret_cast<double2*>(wv + i) = *reinterpret_cast<const double2*>(Wg + i);
+      *reinterpret_cast<double2*>(wrv + i) = *reinterpret_cast<const double2*>(WRg + i);
+    }
+  }
+  for (int l = tid; l < nin; l += T) {
+    const int k = IAg[l];
+    ia[l] = k;
+    aact[l] = AAg[l];
+    xma[l] = XMc[k];
+    xia[l] = XIc[k];
+  }
+  __syncthreads();
+
+  // ---------------- phase A: consume the gradient of the previous round ----------------
+  auto mark_pass = [&](double thresh) -> int {
+    int cnt = 0;
+    for (int j = tid; j < p; j += T) {
+      const double xi = XIc[j];
+      if (xi != 0.0 && MMc[j] == 0) {
+        const double ga = fabs((Gc[j] - XMc[j] * sumr) * xi);
+        if (ga > thresh) {
+          MMc[j] = -1;
+          ++cnt;
+        }
+      }
+    }
+    return __syncthreads_or(cnt);
+  };
+
+  // On a lambda advance the strong set is rebuilt from the sequential strong rule on the fresh
+  // gradient (actives + {ga > 2 lambda_new - lambda_old}) instead of fishnet1's ever-growing ixx:
+  // the full KKT check of the next round still covers every predictor, so the solution is the
+  // same; the per-step strong-set check just stops paying for hundreds of long-dead candidates.
+  auto mark_reset = [&](double thresh) -> int {
+    int cnt = 0;
+    for (int j = tid; j < p; j += T) {
+      const double xi = XIc[j];
+      const int mm = MMc[j];
+      if (xi != 0.0 && mm <= 0) {
+        const double ga = fabs((Gc[j] - XMc[j] * sumr) * xi);
+        const int nm = ga > thresh ? -1 : 0;
+        if (nm != mm) {
+          MMc[j] = nm;
+          ++cnt;
+        }
+      }
+    }
+    return __syncthreads_or(cnt);
+  };
+  bool strong_changed = false;
+  if (state == ST_INIT && (nlam < 1 || A.ws.prob[(size_t)g * A.prm.NF].jerr > 0)) {
+    state = ST_DONE;  // the gene's master fit failed: the whole gene falls back to the mean
+  } else if (state == ST_INIT) {
+    if (master_auto) {
+      double m = 0.0;
+      for (int j = tid; j < p; j += T) {
+        const double xi = XIc[j];
+        if (xi != 0.0) m = fmax(m, fabs((Gc[j] - XMc[j] * sumr) * xi));
+      }
+      m = bmax(m, red, phase);
+      if (tid == 0) {  // the null model is solution 0 (lambda = "big")
+        A.ws.a0p[(size_t)g * kNLam] = az;
+        A.ws.devp[(size_t)g * kNLam] = cur_dev;
+        A.ws.ninp[(size_t)g * kNLam] = 0;
+      }
+      lmu = 1;
+      lidx = 1;
+      al0 = m;
+      al = lamg[1];
+      if (nlam < 2) state = ST_DONE;
+    } else {
+      lidx = 0;
+      al0 = 0.0;
+      al = lamg[0];
+    }
+    if (state != ST_DONE) {
+      strong_changed = mark_pass(2.0 * al - al0) != 0;
+      state = ST_SOLVE;
+    }
+  } else if (state == ST_WAIT_KKT) {
+    if (mark_pass(al)) {
+      strong_changed = true;
+      state = ST_SOLVE;  // KKT violated outside the strong set: re-solve this lambda
+    } else {
+      // ---- commit solution lidx ----
+      if (fit == 0) {
+        const size_t o = (size_t)g * kNLam + lidx;
+        if (tid == 0) {
+          A.ws.a0p[o] = az;
+          A.ws.devp[o] = cur_dev;
+          A.ws.ninp[o] = nin;
+          A.ws.nlpp[o] = nlp;
+        }
+        double* cp = A.ws.cap + o * kNX;
+        for (int l = tid; l < nin; l += T) cp[l] = aact[l];
+      } else if (tid == 0) {
+        A.ws.cvdev[((size_t)g * kNLam + lidx) * kMaxFolds + (fit - 1)] = cur_cv / ncv;
+      }
+      lmu = lidx + 1;
+      bool stop = false;
+      if (master_auto) {
+        const int mnl = kMnLam < nlam ? kMnLam : nlam;
+        if (lidx + 1 >= mnl) {
+          int me = 0;
+          for (int l = tid; l < nin; l += T) me += aact[l] != 0.0;
+          double mv[1] = {(double)me};
+          bsum<1>(mv, red, phase);
+          const double dprev = A.ws.devp[(size_t)g * kNLam + lidx - mnl + 1];
+          if (mv[0] > ne) stop = true;
+          else if ((cur_dev - dprev) / cur_dev < kSml) stop = true;
+          else if (cur_dev > kDevMax) stop = true;
+        }
+      }
+      int lim = nlam;
+      if (is_fold && A.prm.auto_lambda) {
+        const int lf = *reinterpret_cast<volatile int*>(A.ws.Lfinal + g);
+        if (lf < lim) lim = lf;
+      }
+      if (stop || lidx + 1 >= lim) {
+        state = ST_DONE;
+      } else {
+        ++lidx;
+        al0 = al;
+        al = lamg[lidx];
+        strong_changed = mark_reset(al - A.prm.strong_slack * (al0 - al)) != 0;
+        state = ST_SOLVE;
+      }
+    }
+  }
+  if (strong_changed) nS = rebuild_strong<T>(MMc, SIc, p, ish);
+
+  // ---------------- phase B (Gram space): IRLS + coordinate descent on the strong set ----------
+  // Within one IRLS step the working weights are fixed, so the cyclic sweeps over the active set
+  // only need the weighted Gram block H = X~_A^T W X~_A and the gradient q = X~_A^T wr: a
+  // coordinate update is q -= d * H[:, l] on an |A|-vector instead of an n-long dot + axpy with a
+  // block reduction.  H is built once per IRLS step with FP64 DMMA straight from the resident
+  // design; the n-space residual is only materialised before the strong-set check of the inactive
+  // variables (batched dots, no per-variable barrier) and when a variable enters.
+  lap(0);
+  double* H = nullptr;
+  int hslot = -1;
+  if (state == ST_SOLVE) {
+    if (tid == 0) {
+      int sidx = blockIdx.x % kHSlots;
+      while (atomicCAS(A.ws.hflags + sidx, 0, 1) != 0) sidx = (sidx + 1) % kHSlots;
+      ish[41] = sidx;
+    }
+    __syncthreads();
+    hslot = ish[41];
+    H = A.ws.Hs + (size_t)hslot * kNX * kNX;
+  }
+  constexpr int ldh = kNX;
+  constexpr int EPT = (kNX + T - 1) / T;
+  double q0 = 0.0, azmat = az;
+  double v0m = v0;       // sum of the weights the Gram block was built with (the model's v0)
+  bool H_valid = false;  // a Gram block exists for this launch
+  bool H_fresh = false;  // ... and it was built with the current working weights
+  bool dirty = false;
+
+  // p_l = sum w Xs_l -> swa[l], r_l = sum wr Xs_l -> gq[l]   (four columns per reduction)
+  auto gram_vectors = [&](int l0, int l1, bool with_p) {
+    for (int lb = l0; lb < l1; lb += 4) {
+      const double* c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = Xs + (size_t)ia[lb + j < l1 ? lb + j : l1 - 1] * ldx;
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int i = 2 * tid; i < ldx; i += 2 * T) {
+        const double2 w = *reinterpret_cast<const double2*>(wv + i);
+        const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 x = ldg2(c[j] + i);
+          acc[j] += w.x * x.x + w.y * x.y;
+          acc[4 + j] += r.x * x.x + r.y * x.y;
+        }
+      }
+      bsum<8>(acc, red, phase);
+      if (tid < 4 && lb + tid < l1) {
+        if (with_p) swa[lb + tid] = acc[tid];
+        gq[lb + tid] = acc[4 + tid];
+      }
+      ncols += 4;
+    }
+    __syncthreads();
+  };
+  // raw weighted Gram P[l][k] = sum_i w_i Xs_il Xs_ik for l, k < m, 16 x 16 tiles per warp on DMMA
+  auto gram_P = [&](int m) {
+    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2;
+    for (int tix = warp; tix < ntile; tix += nw) {
+      int J = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+      while ((J + 1) * (J + 2) / 2 <= tix) ++J;
+      while (J * (J + 1) / 2 > tix) --J;
+      const int I = tix - J * (J + 1) / 2;
+      auto colp = [&](int idx) { return Xs + (size_t)ia[idx < m ? idx : m - 1] * ldx + 2 * t4; };
+      const double *cI0 = colp(I * 16 + g8), *cI1 = colp(I * 16 + 8 + g8);
+      const double *cJ0 = colp(J * 16 + g8), *cJ1 = colp(J * 16 + 8 + g8);
+      double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+#pragma unroll 2
+      for (int base = 0; base < ldx; base += 8) {
+        const double2 a0 = ldg2(cI0 + base), a1 = ldg2(cI1 + base);
+        double2 b0 = ldg2(cJ0 + base), b1 = ldg2(cJ1 + base);
+        const double2 w = *reinterpret_cast<const double2*>(wv + base + 2 * t4);
+        b0.x *= w.x; b0.y *= w.y; b1.x *= w.x; b1.y *= w.y;
+        dmma(acc[0][0][0], acc[0][0][1], a0.x, b0.x);
+        dmma(acc[0][1][0], acc[0][1][1], a0.x, b1.x);
+        dmma(acc[1][0][0], acc[1][0][1], a1.x, b0.x);
+        dmma(acc[1][1][0], acc[1][1][1], a1.x, b1.x);
+        dmma(acc[0][0][0], acc[0][0][1], a0.y, b0.y);
+        dmma(acc[0][1][0], acc[0][1][1], a0.y, b1.y);
+        dmma(acc[1][0][0], acc[1][0][1], a1.y, b0.y);
+        dmma(acc[1][1][0], acc[1][1][1], a1.y, b1.y);
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = I * 16 + a * 8 + g8, cc = J * 16 + b * 8 + 2 * t4 + e;
+            if (r < m && cc < m && (I != J || r <= cc)) {
+              H[r + (size_t)cc * ldh] = acc[a][b][e];
+              H[cc + (size_t)r * ldh] = acc[a][b][e];
+            }
+          }
+    }
+    gram_fma += (unsigned long long)ntile * 256ull * (unsigned)ldx;
+    __syncthreads();
+  };
+  // per-fit standardisation of the raw moments: H and v (-> va) ...
+  auto gram_finish_H = [&](int m) {
+    for (int idx = tid; idx < m * m; idx += T) {
+      const int r = idx % m, c = idx / m;
+      const double P = H[r + (size_t)c * ldh];
+      H[r + (size_t)c * ldh] =
+          xia[r] * xia[c] * (P - xma[r] * swa[c] - xma[c] * swa[r] + xma[r] * xma[c] * v0);
+    }
+    __syncthreads();
+    for (int l = tid; l < m; l += T) va[l] = H[l + (size_t)l * ldh];
+    __syncthreads();
+  };
+  // ... and of the vectors: q (-> gq) always, h0 (-> swa) when the block was rebuilt
+  auto gram_finish_vec = [&](int m, bool with_p) {
+    for (int l = tid; l < m; l += T) {
+      gq[l] = xia[l] * (gq[l] - xma[l] * q0);  // q0 = current sum of the working residual
+      if (with_p) swa[l] = xia[l] * (swa[l] - xma[l] * v0);
+    }
+    __syncthreads();
+  };
+  // One cyclic sweep over the active set in Gram space.  For m <= 256 the whole sweep runs inside
+  // warp 0 with q in registers (8 entries per lane): a coordinate step is a shuffle broadcast, a
+  // few dependent FP64 operations and 8 FMAs per lane, with the Hessian column prefetched two
+  // steps ahead -- no block barrier inside the sweep.  Larger active sets use the block version.
+  auto gsweep_warp = [&](bool by_index, int m, double& dlx) {
+    if (tid < 32) {
+      if (m <= 128) gram_sweep_warp<4, 3>(H, ldh, m, by_index, ord, gq, va, aact, swa, al, gsh, dlx, q0);
+      else gram_sweep_warp<8, 2>(H, ldh, m, by_index, ord, gq, va, aact, swa, al, gsh, dlx, q0);
+    }
+    __syncthreads();
+    dlx = gsh[0];
+    q0 = gsh[1];
+    if (gsh[2] != 0.0) dirty = true;
+    __syncthreads();
+  };
+  auto gsweep_block = [&](bool by_index, int m, double& dlx) {
+    double hreg[EPT];
+    int lnext = by_index ? ord[0] : 0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int j = tid + e * T;
+      hreg[e] = j < m ? H[j + (size_t)lnext * ldh] : 0.0;
+    }
+    // q is double buffered (gq / gq2): a changed step reads the current buffer and writes the
+    // other one, so one barrier per changed step orders everything
+    double* qa = gq;
+    double* qb = gq2;
+    for (int t = 0; t < m; ++t) {
+      const int l = lnext;
+      double hcur[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) hcur[e] = hreg[e];
+      if (t + 1 < m) {
+        lnext = by_index ? ord[t + 1] : t + 1;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int j = tid + e * T;
+          hreg[e] = j < m ? H[j + (size_t)lnext * ldh] : 0.0;
+        }
+      }
+      const double ql = qa[l], v = va[l], ak = aact[l];
+      const double u = ql + v * ak;
+      const double au = fabs(u) - al;
+      const double anew = au > 0.0 ? copysign(au, u) / v : 0.0;
+      if (anew == ak) continue;
+      if (anew != anew) { dlx = NAN; break; }
+      const double d = anew - ak;
+      dlx = fmax(dlx, v * d * d);
+      q0 -= d * swa[l];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int j = tid + e * T;
+        if (j < m) qb[j] = qa[j] - d * hcur[e];
+      }
+      dirty = true;
+      __syncthreads();
+      if (tid == 0) aact[l] = anew;  // nobody reads aact[l] again before the next barrier
+      double* tq = qa; qa = qb; qb = tq;
+    }
+    __syncthreads();
+    if (qa != gq) {  // leave the result in gq
+      for (int j = tid; j < m; j += T) gq[j] = qa[j];
+    }
+    __syncthreads();
+  };
+  auto gsweep = [&](bool by_index, int m, double& dlx) {
+    if (m == 0) return;
+    tph[8] += m;
+    tph[9] += 1;
+    if (m <= 256) gsweep_warp(by_index, m, dlx);
+    else gsweep_block(by_index, m, dlx);
+  };
+  auto gintercept = [&](int m, double& dlx) {
+    const double d = q0 / v0m;
+    az += d;
+    dlx = fmax(dlx, v0m * d * d);
+    for (int j = tid; j < m; j += T) gq[j] -= d * swa[j];
+    q0 -= d * v0m;
+    if (d != 0.0) dirty = true;
+    __syncthreads();
+  };
+  // bring the n-space residual up to date with the coefficients: wr -= w * (X~_A da + daz)
+  auto materialise = [&](int m) {
+    if (!dirty) return;
+    double sh[1] = {0.0};
+    for (int l = tid; l < m; l += T) {
+      const double c = (aact[l] - amat[l]) * xia[l];
+      amat[l] = c;
+      sh[0] += c * xma[l];
+    }
+    bsum<1>(sh, red, phase);
+    const double shift = (az - azmat) - sh[0];
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      double s0 = shift, s1 = shift;
+#pragma unroll 4
+      for (int l = 0; l < m; ++l) {
+        const double c = amat[l];
+        if (c != 0.0) {
+          const double2 x = ldg2(Xs + (size_t)ia[l] * ldx + i);
+          s0 += c * x.x;
+          s1 += c * x.y;
+        }
+      }
+      const double2 w = *reinterpret_cast<const double2*>(wv + i);
+      double2 r = *reinterpret_cast<const double2*>(wrv + i);
+      r.x -= w.x * s0;
+      r.y -= w.y * s1;
+      *reinterpret_cast<double2*>(wrv + i) = r;
+    }
+    ncols += m;
+    __syncthreads();
+    for (int l = tid; l < m; l += T) amat[l] = aact[l];
+    azmat = az;
+    dirty = false;
+    __syncthreads();
+  };
+  // a strong-set variable enters: n-space coordinate update + one new Gram row/column
+  auto activate = [&](int k, double xm, double xi, double gk, int& m, double& dlx) -> bool {
+    const double* col = Xs + (size_t)k * ldx;
+    double d2[2] = {0.0, 0.0};
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      const double2 x = ldg2(col + i);
+      const double2 w = *reinterpret_cast<const double2*>(wv + i);
+      const double wx0 = w.x * x.x, wx1 = w.y * x.y;
+      d2[0] += wx0 + wx1;
+      d2[1] += wx0 * x.x + wx1 * x.y;
+    }
+    bsum<2>(d2, red, phase);
+    const double sw = xi * (d2[0] - xm * v0);
+    const double v = xi * xi * (d2[1] - 2.0 * xm * d2[0] + xm * xm * v0);
+    const double au = fabs(gk) - al;
+    const double d = copysign(au, gk) / v;
+    if (d != d) { dlx = NAN; return false; }
+    dlx = fmax(dlx, v * d * d);
+    {  // wr -= d * w * x~_k
+      const double c = d * xi;
+      for (int i = 2 * tid; i < ldx; i += 2 * T) {
+        const double2 x = ldg2(col + i);
+        double2 r = *reinterpret_cast<const double2*>(wrv + i);
+        const double2 w = *reinterpret_cast<const double2*>(wv + i);
+        r.x -= c * w.x * (x.x - xm);
+        r.y -= c * w.y * (x.y - xm);
+        *reinterpret_cast<double2*>(wrv + i) = r;
+      }
+    }
+    q0 -= d * sw;
+    ++nin;
+    if (nin > nx) return false;  // pmax overflow, handled by the caller
+    // new Gram column against the m current members (four per reduction)
+    for (int lb = 0; lb < m; lb += 4) {
+      const double* c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = Xs + (size_t)ia[lb + j < m ? lb + j : m - 1] * ldx;
+      double acc[4] = {0, 0, 0, 0};
+      for (int i = 2 * tid; i < ldx; i += 2 * T) {
+        const double2 x = ldg2(col + i);
+        const double2 w = *reinterpret_cast<const double2*>(wv + i);
+        const double wx0 = w.x * x.x, wx1 = w.y * x.y;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 z = ldg2(c[j] + i);
+          acc[j] += wx0 * z.x + wx1 * z.y;
+        }
+      }
+      bsum<4>(acc, red, phase);
+      if (tid < 4 && lb + tid < m) {
+        const int l = lb + tid;
+        const double pl = swa[l] / xia[l] + xma[l] * v0;  // raw sum w Xs_l back from h0_l
+        const double h = xia[l] * xi * (acc[tid] - xma[l] * d2[0] - xm * pl + xma[l] * xm * v0);
+        H[l + (size_t)m * ldh] = h;
+        H[m + (size_t)l * ldh] = h;
+        gq[l] -= d * h;
+      }
+      ncols += 4;
+    }
+    if (tid == 0) {
+      H[m + (size_t)m * ldh] = v;
+      MMc[k] = nin;
+      ia[m] = k;
+      xma[m] = xm;
+      xia[m] = xi;
+      va[m] = v;
+      swa[m] = sw;
+      as_[m] = 0.0;
+      aact[m] = d;
+      amat[m] = d;
+      gq[m] = gk - d * v;
+      int t = m;  // keep ord[] sorted by variable index
+      while (t > 0 && ia[ord[t - 1]] > k) { ord[t] = ord[t - 1]; --t; }
+      ord[t] = m;
+    }
+    ncols += 2;
+    m = nin;
+    __syncthreads();
+    return true;
+  };
+  // Strong-set check of the inactive variables (KKT inside the strong set): batched dots
+  // g_k = x~_k^T wr, eight columns per barrier; a variable whose |g_k| exceeds lambda enters.
+  auto inactive_check = [&](int& m, double& dlx, bool& overflow) {
+    if (ninact == 0) return;
+    tph[10] += ninact;
+    tph[11] += 1;
+    materialise(m);
+    lap(4);
+    int cur = 0;
+    while (cur < ninact) {
+      const int cn = ninact - cur < kMeta ? ninact - cur : kMeta;
+      __syncthreads();
+      if (tid < cn) {
+        const int k = INc[cur + tid];
+        mk[tid] = k;
+        mxm[tid] = XMc[k];
+        mxi[tid] = XIc[k];
+        mpos[tid] = MMc[k];
+      }
+      __syncthreads();
+      int j = 0;
+      while (j < cn) {
+        int nb = 0, jj = j, first = -1, last = j;
+        while (jj < cn && nb < 8) {
+          if (mpos[jj] < 0) { if (first < 0) first = jj; last = jj; ++nb; }
+          ++jj;
+        }
+        if (nb == 0) break;
+        // the batch = the first 8 inactive entries in [first, last]; slot b -> b-th of them
+        const double* c[8];
+        int bi[8];
+        {
+          int b = 0;
+          for (int e = first; e <= last; ++e)
+            if (mpos[e] < 0) { bi[b] = e; c[b] = Xs + (size_t)mk[e] * ldx; ++b; }
+          for (; b < 8; ++b) { bi[b] = bi[nb - 1]; c[b] = c[nb - 1]; }
+        }
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+        for (int i = 2 * tid; i < ldx; i += 2 * T) {
+          const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const double2 x = ldg2(c[b] + i);
+            acc[b] += r.x * x.x + r.y * x.y;
+          }
+        }
+        bsum<8>(acc, red, phase);
+        ncols += nb;
+        int hit = -1;
+        double gk = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const double g1 = mxi[bi[b]] * (acc[b] - mxm[bi[b]] * q0);
+          if (hit < 0 && b < nb && fabs(g1) > al) { hit = b; gk = g1; }
+        }
+        if (hit < 0) {
+          j = jj;
+          continue;
+        }
+        int e = first;  // position of the hit inside the chunk
+        for (int b = 0, ee = first; ee <= last; ++ee)
+          if (mpos[ee] < 0) { if (b == hit) e = ee; ++b; }
+        lap(5);
+        tph[14] += 1;
+        if (!activate(mk[e], mxm[e], mxi[e], gk, m, dlx)) {
+          if (nin > nx) overflow = true;
+          return;
+        }
+        lap(13);
+        if (tid == 0) mpos[e] = nin;
+        __syncthreads();
+        j = e + 1;  // the rest of the batch sees the updated residual
+      }
+      cur += cn;
+    }
+  };
+
+  if (state == ST_SOLVE) {
+    // inactive members of the strong set, in index order
+    {
+      int base = 0;
+      const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+      for (int s0 = 0; s0 < nS; s0 += T) {
+        const int s = s0 + tid;
+        const int k = s < nS ? SIc[s] : 0;
+        const bool flag = s < nS && MMc[k] < 0;
+        const unsigned b = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) ish[warp] = __popc(b);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) {
+          const int c = ish[w];
+          if (w < warp) woff += c;
+          tot += c;
+        }
+        if (flag) INc[base + woff + __popc(b & ((1u << lane) - 1u))] = k;
+        base += tot;
+        __syncthreads();
+      }
+      ninact = base;
+    }
+    // ord[] = active positions sorted by variable index
+    for (int l = tid; l < nin; l += T) {
+      int rank = 0;
+      const int k = ia[l];
+      for (int j = 0; j < nin; ++j) rank += ia[j] < k;
+      ord[rank] = l;
+    }
+    __syncthreads();
+    while (true) {  // IRLS iterations
+      const double az0 = az;
+      for (int l = tid; l < nin; l += T) {
+        as_[l] = aact[l];
+        amat[l] = aact[l];
+      }
+      azmat = az;
+      dirty = false;
+      q0 = sumr;
+      bool overflow = false, maxed = false, nanfail = false;
+      int m = nin;
+      __syncthreads();
+      const int dbg = A.prm.dbg;
+      if (m > 0 && !(dbg & 1)) {
+        // The gradient is exact at every IRLS step.  The Hessian model (Gram block, intercept row
+        // h0, v0) is built once per launch (= once per lambda) and kept for the later IRLS steps
+        // of the same lambda as ONE consistent matrix (a true weighted Gram, so the sweeps cannot
+        // cycle): the fixed point only depends on the gradient, the model only shapes the step
+        // (chord iteration).  A variable entering under a stale model triggers a rebuild.
+        lap(3);
+        const bool rebuild = !H_valid || (dbg & 64);
+        gram_vectors(0, m, rebuild);
+        lap(1);
+        if (rebuild) {
+          gram_P(m);
+          gram_finish_H(m);
+          v0m = v0;
+          H_valid = true;
+        }
+        gram_finish_vec(m, rebuild);
+        H_fresh = rebuild;
+        lap(2);
+      } else if (m == 0) {
+        v0m = v0;
+        H_fresh = true;
+      }
+      tph[7] += 1;
+      tph[12] += m;
+      while (true) {  // strong-set phases until one changes nothing
+        ++nlp;
+        double dlx = 0.0;
+        if (!(dbg & 2)) gsweep(true, m, dlx);
+        lap(3);
+        lap(4);
+        if (!(dbg & 8)) inactive_check(m, dlx, overflow);
+        lap(5);
+        if (overflow) break;
+        gintercept(m, dlx);
+        if (dlx < shr) break;
+        if (!(dlx == dlx)) { nanfail = true; break; }
+        if (nlp > maxit) { maxed = true; break; }
+        int inner = 0;
+        while (true) {  // sweeps over the ever-active list
+          ++nlp;
+          dlx = 0.0;
+          if (!(dbg & 2)) gsweep(false, m, dlx);
+          gintercept(m, dlx);
+          if (dlx < shr) break;
+          if (!(dlx == dlx)) { nanfail = true; break; }
+          if (nlp > maxit) { maxed = true; break; }
+          if (++inner >= 64 && !H_fresh && m > 0) {
+            // A model that mixes weights of several IRLS steps (kept block + rows of variables that
+            // entered later) is not guaranteed to be a Gram matrix; if the sweeps stall, rebuild it
+            // with the current weights (then it is one, and coordinate descent converges).
+            materialise(m);
+            gram_vectors(0, m, true);
+            gram_P(m);
+            gram_finish_H(m);
+            v0m = v0;
+            gram_finish_vec(m, true);
+            H_fresh = true;
+            inner = 0;
+          }
+        }
+        if (maxed || nanfail) break;
+      }
+      if (overflow) { jerr = -10000 - (lidx + 1); state = ST_DONE; break; }
+      if (maxed) { jerr = -(lidx + 1); state = ST_DONE; break; }
+      if (nanfail) { jerr = 9998; state = ST_DONE; break; }
+
+      // ---- re-linearise: f = az + sum_l a_l x~_l, w = q exp(f), wr = t - w ----
+      lap(3);
+      __syncthreads();
+      double c0p[1] = {0.0};
+      for (int l = tid; l < nin; l += T) {
+        const double b = aact[l] * xia[l];
+        gq2[l] = b;  // scratch: gq2 is only live inside a block-mode sweep
+        c0p[0] += b * xma[l];
+      }
+      bsum<1>(c0p, red, phase);
+      const double c0 = az - c0p[0];
+      ncols += nin;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum w, sum t f, sum wr, held-out deviance
+      for (int i = 2 * tid; i < ldx; i += 2 * T) {
+        double f0 = c0, f1 = c0;
+#pragma unroll 4
+        for (int l = 0; l < nin; ++l) {
+          const double b = gq2[l];
+          if (b != 0.0) {
+            const double2 x = ldg2(Xs + (size_t)ia[l] * ldx + i);
+            f0 += b * x.x;
+            f1 += b * x.y;
+          }
+        }
+        double wn[2] = {0.0, 0.0}, rn[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ii = i + e;
+          if (ii < n) {
+            const int f = fo[ii];
+            const double fe = e ? f1 : f0;
+            if (f != 0 && f != fit) {
+              const double yi = y[ii];
+              const double t = qv * yi;
+              const double fc = fabs(fe) < fmax_ ? fe : copysign(fmax_, fe);
+              wn[e] = qv * exp(fc);
+              rn[e] = t - wn[e];
+              acc[0] += wn[e];
+              acc[1] += t * fe;
+              acc[2] += rn[e];
+            } else if (f != 0 && is_fold) {  // held-out row of this fold
+              const double yi = y[ii];
+              const double devy = yi == 0.0 ? 0.0 : yi * log(yi) - yi;
+              acc[3] += 2.0 * (devy - (yi * fe - exp(fe)));
+            }
+          }
+        }
+        *reinterpret_cast<double2*>(wv + i) = make_double2(wn[0], wn[1]);
+        *reinterpret_cast<double2*>(wrv + i) = make_double2(rn[0], rn[1]);
+      }
+      bsum<4>(acc, red, phase);
+      v0 = acc[0];
+      sumr = acc[2];
+      cur_dev = (acc[1] - v0 - dv0) / dvr;
+      cur_cv = acc[3];
+      // ---- outer convergence (fishnet1: intercept and every active coefficient) ----
+      int bad = v0 * (az - az0) * (az - az0) >= shr;
+      for (int l = tid; l < nin; l += T) {
+        const double d = aact[l] - as_[l];
+        bad |= va[l] * d * d >= shr;
+      }
+      lap(6);
+      if (!__syncthreads_or(bad)) {
+        state = ST_WAIT_KKT;
+        break;
+      }
+    }
+  }
+
+  // ---------------- write back ----------------
+  __syncthreads();
+  if (STAGED) {
+    for (int i = 2 * tid; i < ldx; i += 2 * T) {
+      *reinterpret_cast<double2*>(Wg + i) = *reinterpret_cast<const double2*>(wv + i);
+      *reinterpret_cast<double2*>(WRg + i) = *reinterpret_cast<const double2*>(wrv + i);
+    }
+  }
+  for (int l = tid; l < nin && l < kNX; l += T) {
+    IAg[l] = ia[l];
+    AAg[l] = aact[l];
+  }
+  if (state != ST_DONE) {
+    if (tid == 0) {
+      const int pos = atomicAdd(counter, 1);
+      nextlist[pos] = pid;
+      ish[40] = pos;
+    }
+    __syncthreads();
+    const int pos = ish[40];
+    double* r = A.ws.R + (size_t)pos * ldx;
+    for (int i = 2 * tid; i < ldx; i += 2 * T)
+      *reinterpret_cast<double2*>(r + i) = *reinterpret_cast<const double2*>(wrv + i);
+    if (tid == 0) PR->slot = pos;
+  }
+  if (tid == 0 && hslot >= 0) {
+    __threadfence();
+    atomicExch(A.ws.hflags + hslot, 0);
+  }
+  if (tid == 0) {
+    atomicAdd(A.ws.colcount + 4, gram_fma);
+    for (int k = 0; k < 16; ++k) atomicAdd(A.ws.phasecyc + k, (unsigned long long)tph[k]);
+    atomicAdd(A.ws.colcount, (unsigned long long)ncols);
+    const unsigned long long cyc = (unsigned long long)(clock64() - t_start);
+    atomicAdd(A.ws.colcount + 1, cyc);   // sum of CTA lifetimes
+    atomicMax(A.ws.colcount + 2, cyc);   // longest CTA of the block of rounds (straggler)
+    atomicAdd(A.ws.colcount + 3, (unsigned long long)(state == ST_WAIT_KKT || state == ST_DONE));
+    if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
+    PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
+    PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
+    PR->al = al; PR->al0 = al0; PR->az = az; PR->v0 = v0; PR->sumr = sumr;
+    PR->cur_dev = cur_dev; PR->cur_cv = cur_cv;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // finalize: cv.glmnet statistics + lambda.min + prediction for all cells (one CTA per gene)
 // ---------------------------------------------------------------------------------------------
@@ -923,7 +1847,7 @@ __global__ void __launch_bounds__(256) lasso_finalize_kernel(FinalArgs F) {
   const int* IAg = A.ws.IA + pid0 * kNX;
   const double* XMc = A.ws.XM + pid0 * A.p_pad;
   const double* XIc = A.ws.XI + pid0 * A.p_pad;
-  __shared__ double red[256];
+  __shared__ double red[512];
   int phase = 0;
   double sh[1] = {0.0};
   for (int l = tid; l < nmax; l += 256) {
@@ -937,6 +1861,15 @@ __global__ void __launch_bounds__(256) lasso_finalize_kernel(FinalArgs F) {
   bsum<1>(sh, red, phase);
   const double a0 = frac * A.ws.a0p[oL] + (1.0 - frac) * A.ws.a0p[oR] - sh[0];
   __syncthreads();
+  if (!(fabs(a0) < INFINITY)) {  // a non-finite solution is a failed fit: mean prediction
+    const double m = A.ws.gmean[g];
+    for (int i = tid; i < n; i += 256) mu[i] = m;
+    if (tid == 0) {
+      F.out4[4 * g + 0] = 0; F.out4[4 * g + 1] = 0; F.out4[4 * g + 2] = 0; F.out4[4 * g + 3] = -1;
+      F.status[g] = 2;
+    }
+    return;
+  }
   for (int i = tid; i < n; i += 256) {
     double f = a0;
     for (int l = 0; l < nmax; ++l) {
@@ -964,6 +1897,24 @@ cudaError_t launch_round_t(const RoundArgs& A, const int* list, int* nextlist, i
   if (mode == 2) return launch_round_k<T, true, true>(A, list, nextlist, counter, grid, smem, s);
   if (mode == 1) return launch_round_k<T, true, false>(A, list, nextlist, counter, grid, smem, s);
   return launch_round_k<T, false, false>(A, list, nextlist, counter, grid, smem, s);
+}
+
+template <int T>
+cudaError_t launch_gram_t(const RoundArgs& A, const int* list, int* nextlist, int* counter,
+                          int grid, bool staged, size_t smem, cudaStream_t s) {
+  cudaError_t e;
+  if (staged) {
+    e = cudaFuncSetAttribute(lasso_round_gram_kernel<T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lasso_round_gram_kernel<T, true><<<grid, T, smem, s>>>(A, list, nextlist, counter);
+  } else {
+    e = cudaFuncSetAttribute(lasso_round_gram_kernel<T, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lasso_round_gram_kernel<T, false><<<grid, T, smem, s>>>(A, list, nextlist, counter);
+  }
+  return cudaGetLastError();
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1001,7 +1952,9 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oDv = take((size_t)kNLam * B * 8), oNi = take((size_t)kNLam * B * 4), oNp = take((size_t)kNLam * B * 4),
                oCap = take((size_t)kNX * kNLam * B * 8),
                oCv = take((size_t)kNLam * kMaxFolds * B * 8), oL0 = take((size_t)P * 4),
-               oL1 = take((size_t)P * 4), oCt = take(64), oCc = take(64);
+               oL1 = take((size_t)P * 4), oCt = take(64), oCc = take(64),
+               oIn = take((size_t)p_pad * P * 4), oHf = take((size_t)kHSlots * 4),
+               oHs = take((size_t)kHSlots * kNX * kNX * 8), oPh = take(128);
   cudaError_t e;
   if (off > ws.cap_bytes) {
     if (ws.base) {
@@ -1024,15 +1977,22 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   ws.ninp = (int*)(b + oNi); ws.nlpp = (int*)(b + oNp); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
   ws.list0 = (int*)(b + oL0); ws.list1 = (int*)(b + oL1); ws.counters = (int*)(b + oCt);
   ws.colcount = (unsigned long long*)(b + oCc);
+  ws.INACT = (int*)(b + oIn); ws.hflags = (int*)(b + oHf); ws.Hs = (double*)(b + oHs);
+  ws.phasecyc = (unsigned long long*)(b + oPh);
   for (auto& ev : ws.ev)
     if (!ev && (e = cudaEventCreate(&ev)) != cudaSuccess) return e;
 
   RoundArgs A;
   A.Xs = D.Xs; A.xsd = D.xsd; A.n = n; A.ldx = ldx; A.p = D.p; A.p_pad = p_pad; A.P = P;
-  A.prm = prm; A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
+  A.prm = prm;
+  if (const char* e = getenv("SAVER_LASSO_DBG")) A.prm.dbg = atoi(e);
+  if (const char* e = getenv("SAVER_STRONG_SLACK")) A.prm.strong_slack = atof(e);
+  A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
 
   if ((e = cudaMemsetAsync(ws.counters, 0, 64, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ws.colcount, 0, 64, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.hflags, 0, (size_t)kHSlots * 4, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.phasecyc, 0, 128, s)) != cudaSuccess) return e;
   cudaEventRecord(ws.ev[0], s);
   // the padding columns of the GEMM panel must hold finite numbers
   if (P_pad > P &&
@@ -1062,7 +2022,13 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   const size_t smem_x = kFixedSmem + (size_t)4 * ldx * 8, smem_s = kFixedSmem + (size_t)2 * ldx * 8;
   const int mode = smem_x <= 113 * 1024 ? 2 : smem_s <= 227 * 1024 ? 1 : 0;
   const size_t smem = mode == 2 ? smem_x : mode == 1 ? smem_s : kFixedSmem;
+  bool gram = prm.gram != 0;
+  if (const char* e = getenv("SAVER_LASSO_GRAM")) gram = atoi(e) != 0;
+  const size_t smem_g = kFixedSmem + kGramSmem + (size_t)2 * ldx * 8;
+  const bool gram_staged = smem_g <= 227 * 1024;
   int T = ldx <= 2048 ? 128 : ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
+  if (gram) T = ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
+  if (gram) if (const char* e = getenv("SAVER_GRAM_THREADS")) T = atoi(e);
   if (const char* e = getenv("SAVER_LASSO_THREADS")) T = atoi(e);  // tuning experiments only
   if (T != 128 && T != 256 && T != 512 && T != 1024) return cudaErrorInvalidValue;
   int cur = 0;
@@ -1084,6 +2050,15 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     int* cnt = ws.counters + (cur ? 0 : 1);
     if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
     cudaEventRecord(ws.ev[0], s);
+    if (gram) {
+      const size_t sm = gram_staged ? smem_g : kFixedSmem + kGramSmem;
+      switch (T) {
+        case 128: e = launch_gram_t<128>(A, list, next, cnt, live, gram_staged, sm, s); break;
+        case 256: e = launch_gram_t<256>(A, list, next, cnt, live, gram_staged, sm, s); break;
+        case 512: e = launch_gram_t<512>(A, list, next, cnt, live, gram_staged, sm, s); break;
+        default: e = launch_gram_t<1024>(A, list, next, cnt, live, gram_staged, sm, s); break;
+      }
+    } else
     switch (T) {
       case 128: e = launch_round_t<128>(A, list, next, cnt, live, mode, smem, s); break;
       case 256: e = launch_round_t<256>(A, list, next, cnt, live, mode, smem, s); break;
@@ -1118,10 +2093,14 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     }
   }
   {
-    unsigned long long cc[4] = {0, 0, 0, 0};
-    if ((e = cudaMemcpyAsync(cc, ws.colcount, 32, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    unsigned long long cc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if ((e = cudaMemcpyAsync(cc, ws.colcount, 64, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     ws.cols_streamed += cc[0];
+    ws.gram_fma += cc[4];
+    unsigned long long ph[16];
+    if ((e = cudaMemcpy(ph, ws.phasecyc, 128, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    for (int k = 0; k < 16; ++k) ws.phase_cycles[k] += ph[k];
     ws.cta_cycles += cc[1];
     if (cc[2] > ws.max_cta_cycles) ws.max_cta_cycles = cc[2];
   }

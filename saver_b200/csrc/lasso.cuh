@@ -45,6 +45,9 @@ struct LassoParams {
   int maxit;        // glmnet maxit
   double alf_wide;  // lambda ratio for flmin = 0.01 (nobs < nvars), computed on the host
   double alf_tall;  // lambda ratio for flmin = 1e-4
+  int gram = 1;     // 1: Gram-space round kernel (default), 0: n-space kernel that mirrors fishnet1's iterate sequence
+  double strong_slack = 1.0;  // screening margin below lambda in units of the lambda step (1 = strong rule)
+  int dbg = 0;      // bisection switches for bring-up (SAVER_LASSO_DBG), 0 in production
 };
 
 // Device workspace of one block of problems (owned by the handle, grown on demand).
@@ -69,11 +72,16 @@ struct LassoWs {
   double *cvdev;             // kNLam x kMaxFolds x B held-out mean deviance
   int *list0, *list1;        // P each: active problem lists (ping-pong)
   int *counters;             // [2]
-  unsigned long long* colcount;  // design columns streamed by the round kernels (cumulative)
+  unsigned long long* colcount;  // [0] design columns streamed, [1] CTA cycles, [2] max, [3] exits, [4] Gram FMAs
+  int *INACT;                // p_pad x P: inactive members of the strong set (gram kernel)
+  int *hflags;               // Gram scratch slot flags
+  double *Hs;                // Gram scratch: kHSlots x kNX x kNX
+  unsigned long long* phasecyc;  // [8] per-phase SM cycles of the gram kernel (bring-up / profiles)
   // accounting (host side, cumulative over the handle's life)
   double ms_round = 0, ms_gemm = 0, ms_setup = 0;
-  unsigned long long cols_streamed = 0, cta_cycles = 0, max_cta_cycles = 0;
+  unsigned long long cols_streamed = 0, cta_cycles = 0, max_cta_cycles = 0, gram_fma = 0;
   long long rounds = 0;
+  unsigned long long phase_cycles[16] = {0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void release();
 };

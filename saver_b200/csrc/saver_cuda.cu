@@ -292,6 +292,7 @@ int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int
   LassoParams prm;
   prm.NF = nfolds + 1; prm.nfolds = nfolds; prm.auto_lambda = 1; prm.dfmax = dfmax;
   prm.nlam = nlambda; prm.thr = thresh; prm.maxit = 100000;
+  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg;
   prm.alf_wide = lambda_ratio(0.01, nlambda);
   prm.alf_tall = lambda_ratio(1e-4, nlambda);
   const int chunk = lasso_max_block(prm.NF);
@@ -362,7 +363,8 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
   CU(oStats.bind(stats, (size_t)4 * B, dev, s));
   LassoParams prm;
   prm.NF = 1; prm.nfolds = 0; prm.auto_lambda = 0; prm.dfmax = dfmax; prm.nlam = 0;
-  prm.thr = thresh; prm.maxit = 100000; prm.alf_wide = prm.alf_tall = 1.0;
+  prm.thr = thresh; prm.maxit = 100000;
+  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.alf_wide = prm.alf_tall = 1.0;
   const int chunk = lasso_max_block(prm.NF);
   DevBuf<int> fold;
   DevBuf<double> fit4;
@@ -384,6 +386,15 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
 }
 
 long long saver_cuda_gemm_columns(saver_cuda_handle h) { return h ? h->gemm_cols : 0; }
+
+int saver_cuda_set_option(saver_cuda_handle h, const char* key, double value) {
+  if (!h || !key) return SAVER_ERR_ARG;
+  if (!strcmp(key, "lasso_gram")) h->opt_gram = value != 0;
+  else if (!strcmp(key, "strong_slack")) h->opt_strong_slack = value;
+  else if (!strcmp(key, "lasso_dbg")) h->opt_dbg = (int)value;
+  else return fail(h, SAVER_ERR_ARG, "set_option: unknown key %s", key);
+  return SAVER_OK;
+}
 
 int saver_cuda_debug_path(saver_cuda_handle h, int g, double* a0, double* dev, int* nin, int* nlp,
                           double* lam) {
@@ -409,11 +420,17 @@ int saver_cuda_counters(saver_cuda_handle h, double* out8) {
   return SAVER_OK;
 }
 
+int saver_cuda_phase_cycles(saver_cuda_handle h, double* out8) {
+  if (!h || !out8) return SAVER_ERR_ARG;
+  for (int k = 0; k < 16; ++k) out8[k] = (double)h->lasso.phase_cycles[k];
+  return SAVER_OK;
+}
+
 int saver_cuda_counters_ext(saver_cuda_handle h, double* out4) {
   if (!h || !out4) return SAVER_ERR_ARG;
   out4[0] = (double)h->lasso.cta_cycles;
   out4[1] = (double)h->lasso.max_cta_cycles;
-  out4[2] = 0;
+  out4[2] = (double)h->lasso.gram_fma;
   out4[3] = 0;
   return SAVER_OK;
 }

