@@ -224,6 +224,9 @@ def run_cuda(args):
         t = torch.tensor([tmax, e2e_max], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tmax, e2e_max = float(t[0]), float(t[1])
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     total_genes = ngenes_step * world * args.steps
