@@ -141,16 +141,13 @@ def draw_folds(seeds, N, nfolds=5, fold_seed=0, method="philox"):
 
     seeds: the per-gene ``j`` of R/calc_estimate.R:98 (1-based position inside the stage block).
     method "philox": counter-based stream keyed on (fold_seed, j) -- reproducible and independent
-    of how genes are split over blocks or GPUs.  method "R": base R's set.seed(j); sample(...)
-    (Mersenne-Twister + rejection sampling, saver_b200.rrng)."""
+    of how genes are split over blocks or GPUs.  (An R host draws the folds itself with
+    set.seed(j); sample(...), see INTEGRATION.md.)"""
     seeds = np.asarray(seeds, dtype=np.int64)
     base = (np.arange(N) % nfolds + 1).astype(np.int32)
     out = np.empty((seeds.size, N), dtype=np.int32)
-    if method == "R":
-        from . import rrng
-        for i, j in enumerate(seeds):
-            out[i] = base[rrng.sample_perm(int(j), N)]
-        return out
+    if method != "philox":
+        raise SaverError("unknown fold method %r" % (method,))
     for i, j in enumerate(seeds):
         rng = np.random.Generator(np.random.Philox(key=[int(fold_seed) & (2**63 - 1), int(j)]))
         out[i] = base[np.argsort(rng.random(N), kind="stable")]
