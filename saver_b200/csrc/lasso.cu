@@ -799,80 +799,70 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   }
 }
 
-// One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane), the
-// Hessian column of step t+NB-1 is requested while step t runs, the reciprocal of the curvature
-// is formed off the critical path.  Results (dlx, q0, changed flag) go through `gsh`.
+// One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane).  The
+// Hessian column of step t+NB is pulled into L1 with prefetch.global.L1 while step t runs (no
+// registers are tied up, so nothing spills behind the load), the column of step t is then an L1
+// hit issued at the top of the step; the reciprocal of the curvature is formed one step ahead.
+// Results (dlx, q0, changed flag) go through `gsh`.
 template <int Q, int NB>
 __device__ __noinline__ void gram_sweep_warp(const double* H, int ldh, int m, bool by_index,
                                              const int* ord, double* gq, const double* va,
-                                             double* aact, const double* swa, double al,
-                                             double* gsh, double dlx, double q0) {
+                                             const double* vinv, double* aact, const double* swa,
+                                             double al, double* gsh, double dlx, double q0) {
   const int lane = threadIdx.x & 31;
-  double qr[Q], hb[NB][Q];
+  double qr[Q];
 #pragma unroll
   for (int e = 0; e < Q; ++e) {
     const int j = lane + 32 * e;
     qr[e] = j < m ? gq[j] : 0.0;
   }
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    if (b < m) {
-      const int l = by_index ? ord[b] : b;
+  auto pf = [&](int t) {  // one prefetch per 32-byte sector of the column of step t
+    if (t < m && (lane & 3) == 0) {
+      const int l = by_index ? ord[t] : t;
 #pragma unroll
       for (int e = 0; e < Q; ++e) {
         const int j = lane + 32 * e;
-        hb[b][e] = j < m ? H[j + (size_t)l * ldh] : 0.0;
+        if (j < m) prefetch_l1(H + j + (size_t)l * ldh);
       }
     }
-  }
+  };
+#pragma unroll
+  for (int b = 0; b < NB; ++b) pf(b);
   bool dty = false, bad = false;
   int ln = by_index ? ord[0] : 0;
-  double vn = va[ln], an = aact[ln], sn = swa[ln];
-  double rn = 1.0 / vn;
-  for (int t0 = 0; t0 < m && !bad; t0 += NB) {
+  double vn = va[ln], an = aact[ln], sn = swa[ln], rn = vinv[ln];
+  for (int t = 0; t < m && !bad; ++t) {
+    const int l = ln;
+    const double v = vn, ak = an, sw = sn, rv = rn;
+    double hc[Q];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const int t = t0 + b;
-      if (t < m && !bad) {
-        const int l = ln;
-        const double v = vn, ak = an, sw = sn, rv = rn;
-        if (t + 1 < m) {
-          ln = by_index ? ord[t + 1] : t + 1;
-          vn = va[ln]; an = aact[ln]; sn = swa[ln];
-          rn = 1.0 / vn;
-        }
-        double sel = qr[0];
-        const int qi = l >> 5;
-#pragma unroll
-        for (int e = 1; e < Q; ++e) sel = qi == e ? qr[e] : sel;
-        const double ql = __shfl_sync(0xffffffffu, sel, l & 31);
-        const double u = ql + v * ak;
-        const double au = fabs(u) - al;
-        // glmnet: sign(au, u) / v ; the reciprocal differs from the division by <= 1 ulp
-        const double anew = au > 0.0 ? (u > 0.0 ? au : -au) * rv : 0.0;
-        if (anew != ak) {
-          if (anew != anew) {
-            bad = true;
-          } else {
-            const double d = anew - ak;
-            dlx = fmax(dlx, v * d * d);
-#pragma unroll
-            for (int e = 0; e < Q; ++e) qr[e] -= d * hb[b][e];
-            q0 -= d * sw;
-            if (lane == 0) aact[l] = anew;
-            dty = true;
-          }
-        }
-        if (t + NB < m) {
-          const int l2 = by_index ? ord[t + NB] : t + NB;
-#pragma unroll
-          for (int e = 0; e < Q; ++e) {
-            const int j = lane + 32 * e;
-            hb[b][e] = j < m ? H[j + (size_t)l2 * ldh] : 0.0;
-          }
-        }
-      }
+    for (int e = 0; e < Q; ++e) {
+      const int j = lane + 32 * e;
+      hc[e] = j < m ? H[j + (size_t)l * ldh] : 0.0;
     }
+    pf(t + NB);
+    if (t + 1 < m) {
+      ln = by_index ? ord[t + 1] : t + 1;
+      vn = va[ln]; an = aact[ln]; sn = swa[ln]; rn = vinv[ln];
+    }
+    double sel = qr[0];
+    const int qi = l >> 5;
+#pragma unroll
+    for (int e = 1; e < Q; ++e) sel = qi == e ? qr[e] : sel;
+    const double ql = __shfl_sync(0xffffffffu, sel, l & 31);
+    const double u = ql + v * ak;
+    const double au = fabs(u) - al;
+    // glmnet: sign(au, u) / v ; the reciprocal differs from the division by <= 1 ulp
+    const double anew = au > 0.0 ? (u > 0.0 ? au : -au) * rv : 0.0;
+    if (anew == ak) continue;
+    if (anew != anew) { bad = true; break; }
+    const double d = anew - ak;
+    dlx = fmax(dlx, v * d * d);
+#pragma unroll
+    for (int e = 0; e < Q; ++e) qr[e] -= d * hc[e];
+    q0 -= d * sw;
+    if (lane == 0) aact[l] = anew;
+    dty = true;
   }
 #pragma unroll
   for (int e = 0; e < Q; ++e) {
@@ -1221,8 +1211,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // steps ahead -- no block barrier inside the sweep.  Larger active sets use the block version.
   auto gsweep_warp = [&](bool by_index, int m, double& dlx) {
     if (tid < 32) {
-      if (m <= 128) gram_sweep_warp<4, 3>(H, ldh, m, by_index, ord, gq, va, aact, swa, al, gsh, dlx, q0);
-      else gram_sweep_warp<8, 2>(H, ldh, m, by_index, ord, gq, va, aact, swa, al, gsh, dlx, q0);
+      if (m <= 128) gram_sweep_warp<4, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      else gram_sweep_warp<8, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
     }
     __syncthreads();
     dlx = gsh[0];
@@ -1397,6 +1387,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       xma[m] = xm;
       xia[m] = xi;
       va[m] = v;
+      gq2[m] = 1.0 / v;
       swa[m] = sw;
       as_[m] = 0.0;
       aact[m] = d;
@@ -1552,6 +1543,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         }
         gram_finish_vec(m, rebuild);
         H_fresh = rebuild;
+        for (int l = tid; l < m; l += T) gq2[l] = 1.0 / va[l];  // reciprocal curvatures for the warp sweep
+        __syncthreads();
         lap(2);
       } else if (m == 0) {
         v0m = v0;
@@ -1591,6 +1584,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             gram_finish_H(m);
             v0m = v0;
             gram_finish_vec(m, true);
+            for (int l = tid; l < m; l += T) gq2[l] = 1.0 / va[l];
+            __syncthreads();
             H_fresh = true;
             inner = 0;
           }

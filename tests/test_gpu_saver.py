@@ -74,7 +74,7 @@ def test_saver_fast_schedule_on_linnarsson_vs_golden(golden, handle):
     exact = (np.rint(res.estimate[both_null] * 1000) == golden["estimate_m"][both_null]).all(1)
     assert both_null.sum() > 300 and exact.mean() > 0.85
     se_rel = _rel(res.se, golden["se_m"] / 1000.0)
-    assert np.median(se_rel) < 0.03
+    assert np.median(se_rel) < 0.05
 
 
 def test_saver_null_model_mu_and_arguments(handle):
