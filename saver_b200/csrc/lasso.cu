@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kMeta = 64;  // strong-set metadata staged per chunk
 constexpr int kHSlots = 148 * 4;  // Gram scratch slots (>= resident CTAs of the gram kernel)
-constexpr int kGramSmem = 3 * kNX * 8 + 64 + kNX * 4;  // gq, gq2, amat, gsh, ord
+constexpr int kGramSmem = kMeta * 8 + 3 * kNX * 8 + 64 + kNX * 4;  // mg, gq, gq2, amat, gsh, ord
 constexpr int kFixedSmem = 512 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4 + kMeta * (8 + 8 + 4 + 4) + 16;
 
 template <int T>
@@ -896,7 +896,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   double* mxi = mxm + kMeta;
   int* mk = reinterpret_cast<int*>(mxi + kMeta);
   int* mpos = mk + kMeta + 4;  // mk has one extra slot: first column of the next chunk
-  double* gq = reinterpret_cast<double*>(mpos + kMeta);  // gradient on the active set
+  double* mg = reinterpret_cast<double*>(mpos + kMeta);  // staged strong-set gradients
+  double* gq = mg + kMeta;                                // gradient on the active set
   double* gq2 = gq + kNX;                                  // second buffer of the gradient
   double* amat = gq2 + kNX;                                // coefficients at the last materialisation
   double* gsh = amat + kNX;                                // 8 doubles: sweep results broadcast from warp 0
@@ -1116,29 +1117,29 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   bool dirty = false;
 
   // p_l = sum w Xs_l -> swa[l], r_l = sum wr Xs_l -> gq[l]   (four columns per reduction)
+  // (one warp per column, independent accumulators per lane, no block barrier inside)
   auto gram_vectors = [&](int l0, int l1, bool with_p) {
-    for (int lb = l0; lb < l1; lb += 4) {
-      const double* c[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c[j] = Xs + (size_t)ia[lb + j < l1 ? lb + j : l1 - 1] * ldx;
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int i = 2 * tid; i < ldx; i += 2 * T) {
+    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    for (int l = l0 + warp; l < l1; l += nw) {
+      const double* c = Xs + (size_t)ia[l] * ldx;
+      double pa = 0.0, pb = 0.0, ra = 0.0, rb = 0.0;
+#pragma unroll 4
+      for (int i = 2 * lane; i < ldx; i += 64) {
+        const double2 x = ldg2(c + i);
         const double2 w = *reinterpret_cast<const double2*>(wv + i);
         const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double2 x = ldg2(c[j] + i);
-          acc[j] += w.x * x.x + w.y * x.y;
-          acc[4 + j] += r.x * x.x + r.y * x.y;
-        }
+        pa += w.x * x.x;
+        pb += w.y * x.y;
+        ra += r.x * x.x;
+        rb += r.y * x.y;
       }
-      bsum<8>(acc, red, phase);
-      if (tid < 4 && lb + tid < l1) {
-        if (with_p) swa[lb + tid] = acc[tid];
-        gq[lb + tid] = acc[4 + tid];
+      const double ps = warp_sum(pa + pb), rs = warp_sum(ra + rb);
+      if (lane == 0) {
+        if (with_p) swa[l] = ps;
+        gq[l] = rs;
       }
-      ncols += 4;
     }
+    ncols += l1 - l0;
     __syncthreads();
   };
   // raw weighted Gram P[l][k] = sum_i w_i Xs_il Xs_ik for l, k < m, 16 x 16 tiles per warp on DMMA
@@ -1353,32 +1354,31 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     q0 -= d * sw;
     ++nin;
     if (nin > nx) return false;  // pmax overflow, handled by the caller
-    // new Gram column against the m current members (four per reduction)
-    for (int lb = 0; lb < m; lb += 4) {
-      const double* c[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c[j] = Xs + (size_t)ia[lb + j < m ? lb + j : m - 1] * ldx;
-      double acc[4] = {0, 0, 0, 0};
-      for (int i = 2 * tid; i < ldx; i += 2 * T) {
-        const double2 x = ldg2(col + i);
-        const double2 w = *reinterpret_cast<const double2*>(wv + i);
-        const double wx0 = w.x * x.x, wx1 = w.y * x.y;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double2 z = ldg2(c[j] + i);
-          acc[j] += wx0 * z.x + wx1 * z.y;
+    // new Gram column against the m current members: one warp per member, no block barrier
+    {
+      const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+      for (int l = warp; l < m; l += nw) {
+        const double* c = Xs + (size_t)ia[l] * ldx;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+        for (int i = 2 * lane; i < ldx; i += 64) {
+          const double2 x = ldg2(col + i);
+          const double2 z = ldg2(c + i);
+          const double2 w = *reinterpret_cast<const double2*>(wv + i);
+          s0 += w.x * x.x * z.x;
+          s1 += w.y * x.y * z.y;
+        }
+        const double acc = warp_sum(s0 + s1);
+        if (lane == 0) {
+          const double pl = swa[l] / xia[l] + xma[l] * v0m;  // raw sum w Xs_l back from h0_l
+          const double h = xia[l] * xi * (acc - xma[l] * d2[0] - xm * pl + xma[l] * xm * v0);
+          H[l + (size_t)m * ldh] = h;
+          H[m + (size_t)l * ldh] = h;
+          gq[l] -= d * h;
         }
       }
-      bsum<4>(acc, red, phase);
-      if (tid < 4 && lb + tid < m) {
-        const int l = lb + tid;
-        const double pl = swa[l] / xia[l] + xma[l] * v0;  // raw sum w Xs_l back from h0_l
-        const double h = xia[l] * xi * (acc[tid] - xma[l] * d2[0] - xm * pl + xma[l] * xm * v0);
-        H[l + (size_t)m * ldh] = h;
-        H[m + (size_t)l * ldh] = h;
-        gq[l] -= d * h;
-      }
-      ncols += 4;
+      ncols += m;
+      __syncthreads();
     }
     if (tid == 0) {
       H[m + (size_t)m * ldh] = v;
@@ -1402,14 +1402,16 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     __syncthreads();
     return true;
   };
-  // Strong-set check of the inactive variables (KKT inside the strong set): batched dots
-  // g_k = x~_k^T wr, eight columns per barrier; a variable whose |g_k| exceeds lambda enters.
+  // Strong-set check of the inactive variables (KKT inside the strong set): g_k = x~_k^T wr for a
+  // staged chunk of candidates, one warp per column; the first variable (in index order) whose
+  // |g_k| exceeds lambda enters, after which the rest of the chunk is evaluated again.
   auto inactive_check = [&](int& m, double& dlx, bool& overflow) {
     if (ninact == 0) return;
     tph[10] += ninact;
     tph[11] += 1;
     materialise(m);
     lap(4);
+    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
     int cur = 0;
     while (cur < ninact) {
       const int cn = ninact - cur < kMeta ? ninact - cur : kMeta;
@@ -1422,59 +1424,41 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         mpos[tid] = MMc[k];
       }
       __syncthreads();
-      int j = 0;
-      while (j < cn) {
-        int nb = 0, jj = j, first = -1, last = j;
-        while (jj < cn && nb < 8) {
-          if (mpos[jj] < 0) { if (first < 0) first = jj; last = jj; ++nb; }
-          ++jj;
-        }
-        if (nb == 0) break;
-        // the batch = the first 8 inactive entries in [first, last]; slot b -> b-th of them
-        const double* c[8];
-        int bi[8];
-        {
-          int b = 0;
-          for (int e = first; e <= last; ++e)
-            if (mpos[e] < 0) { bi[b] = e; c[b] = Xs + (size_t)mk[e] * ldx; ++b; }
-          for (; b < 8; ++b) { bi[b] = bi[nb - 1]; c[b] = c[nb - 1]; }
-        }
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 2
-        for (int i = 2 * tid; i < ldx; i += 2 * T) {
-          const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const double2 x = ldg2(c[b] + i);
-            acc[b] += r.x * x.x + r.y * x.y;
+      int j0 = 0;
+      while (j0 < cn) {
+        for (int j = j0 + warp; j < cn; j += nw) {
+          if (mpos[j] < 0) {
+            const double* c = Xs + (size_t)mk[j] * ldx;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+            for (int i = 2 * lane; i < ldx; i += 64) {
+              const double2 x = ldg2(c + i);
+              const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+              s0 += r.x * x.x;
+              s1 += r.y * x.y;
+            }
+            const double acc = warp_sum(s0 + s1);
+            if (lane == 0) mg[j] = mxi[j] * (acc - mxm[j] * q0);
           }
         }
-        bsum<8>(acc, red, phase);
-        ncols += nb;
+        __syncthreads();
         int hit = -1;
-        double gk = 0.0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const double g1 = mxi[bi[b]] * (acc[b] - mxm[bi[b]] * q0);
-          if (hit < 0 && b < nb && fabs(g1) > al) { hit = b; gk = g1; }
-        }
-        if (hit < 0) {
-          j = jj;
-          continue;
-        }
-        int e = first;  // position of the hit inside the chunk
-        for (int b = 0, ee = first; ee <= last; ++ee)
-          if (mpos[ee] < 0) { if (b == hit) e = ee; ++b; }
+        for (int j = j0; j < cn; ++j)
+          if (mpos[j] < 0) {
+            ++ncols;
+            if (fabs(mg[j]) > al) { hit = j; break; }
+          }
+        if (hit < 0) break;
         lap(5);
         tph[14] += 1;
-        if (!activate(mk[e], mxm[e], mxi[e], gk, m, dlx)) {
+        if (!activate(mk[hit], mxm[hit], mxi[hit], mg[hit], m, dlx)) {
           if (nin > nx) overflow = true;
           return;
         }
         lap(13);
-        if (tid == 0) mpos[e] = nin;
+        if (tid == 0) mpos[hit] = nin;
         __syncthreads();
-        j = e + 1;  // the rest of the batch sees the updated residual
+        j0 = hit + 1;  // the rest of the chunk sees the updated residual
       }
       cur += cn;
     }

@@ -31,7 +31,7 @@ for it in range(2):
         tot = d_ph[:7].sum()
         print('  phases:', ' '.join('%s %.1f%%' % (n_, 100 * v / tot) for n_, v in zip(names, d_ph[:7])), 'IRLS/gene %.0f' % (d_ph[7] / G), 'cyc/IRLS %.0f' % (tot / d_ph[7]))
         print('  steps/IRLS %.0f sweeps/IRLS %.1f cyc/step %.0f | inactive cols/IRLS %.0f checks/IRLS %.2f cyc/col %.0f | mean m %.0f' % (d_ph[8]/d_ph[7], d_ph[9]/d_ph[7], d_ph[3]/max(d_ph[8],1), d_ph[10]/d_ph[7], d_ph[11]/d_ph[7], d_ph[5]/max(d_ph[10],1), d_ph[12]/d_ph[7]))
-        print('  activations/IRLS %.2f cyc/activation %.0f (%.1f%% of total)' % (d_ph[14]/d_ph[7], d_ph[13]/max(d_ph[14],1), 100*d_ph[13]/(tot+d_ph[13])))
+        print('  activations/IRLS %.2f cyc/activation %.0f (%.1f%% of total)' % (d_ph[14]/d_ph[7], d_ph[13]/max(d_ph[14],1), 100*d_ph[13]/(tot+d_ph[13])), 'first part cyc %.0f' % (d_ph[15]/max(d_ph[14],1)))
     ph_prev = ph
     print('  gram TFLOP %.3g ;' % (2 * (e1[2] - e0[2]) / 1e12), end='')
     print('  cycles/pass (CTA lifetime) %.0f ; slot utilisation (2 CTA/SM) %.2f ; passes/gene %.3g ; sweeps/gene %.0f lmu mean %.1f' % (
