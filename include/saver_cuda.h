@@ -174,6 +174,21 @@ SAVER_API int saver_cuda_cor_adjust(saver_cuda_handle h, const double* est, cons
                                     int G, int by_cells, const double* cor_in, int col0, int ncols,
                                     double* out, int device_ptrs);
 
+/* ---- sparse counts: R's dgCMatrix (genes x cells, compressed by cell: slots p, i, x) ----
+ * Uploaded once and kept resident.  Values < 0.001 are zeroed on upload (clean.data,
+ * R/utils.R:11-19).  Host pointers. */
+SAVER_API int saver_cuda_set_counts_csc(saver_cuda_handle h, const int* indptr, const int* indices,
+                                        const double* data, int G, int n);
+/* colSums (n) and rowSums (G) of the resident matrix: calc.size.factor (R/utils.R:72), the
+ * rowMeans >= 0.1 filter (R/saver.R:156), get.pred.genes (R/utils.R:100-115).  Host outputs. */
+SAVER_API int saver_cuda_csc_sums(saver_cuda_handle h, double* col_sums, double* row_sums);
+/* Dense gene-major panel of B genes (as.matrix(x[block, ]) of R/calc_estimate.R:69): out is n x B.
+ * transform 0: raw counts; 1: log((x + 1) / sf), i.e. rows of x.est (R/saver.R:157).  gene_idx and
+ * sf are host arrays; out lives on the device when out_on_device != 0 (feed it to
+ * saver_cuda_set_design / saver_cuda_calc_estimate with device_ptrs = 1). */
+SAVER_API int saver_cuda_csc_gather(saver_cuda_handle h, const int* gene_idx, int B, const double* sf,
+                                    int transform, double* out, int out_on_device);
+
 /* Problem columns pushed through the gradient GEMM so far (roofline accounting in bench.py):
  * every column is one 2 * n * p flop contraction against the resident design. */
 SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);
@@ -190,6 +205,8 @@ SAVER_API int saver_cuda_counters_ext(saver_cuda_handle h, double* out4);
  * check, [6] re-linearisation, [7] number of IRLS steps, [8] Gram-space coordinate steps, [9] sweeps,
  * [10] strong-set columns checked, [11] checks, [12] sum of |A| over IRLS steps; out has 16 slots. */
 SAVER_API int saver_cuda_phase_cycles(saver_cuda_handle h, double* out16);
+/* Gram-space coordinate steps by active-set size (20 buckets of 32), counted with lasso_dbg bit 128. */
+SAVER_API int saver_cuda_sweep_hist(saver_cuda_handle h, double* out20);
 
 /* Solver options.  "lasso_gram" (default 1): 1 = Gram-space round kernel; 0 = the n-space kernel
  * that follows glmnet's fishnet1 sweep for sweep (slower; agrees with the CPU oracle to rounding on

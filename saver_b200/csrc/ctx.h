@@ -20,6 +20,10 @@ struct saver_cuda_ctx {
   char err[512] = {0};
   saver::DesignState design;
   saver::LassoWs lasso;
+  // resident sparse counts (sparse.cu)
+  int *csc_indptr = nullptr, *csc_indices = nullptr, *csc_map = nullptr;
+  double* csc_data = nullptr;
+  int csc_G = 0, csc_n = 0;
 };
 
 inline int fail(saver_cuda_ctx* h, int code, const char* fmt, ...) {

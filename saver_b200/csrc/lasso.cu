@@ -28,6 +28,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "saver_kernels.h"
@@ -57,6 +60,8 @@ struct RoundArgs {
   const double* Yn;   // n x B (ld = n) normalised expression
   const int* fold;    // n x B: 0 = not a pred cell, 1..nfolds (path variant: any non-zero)
   const int* self;    // B or null
+  int mh;             // largest active set whose packed Gram block fits the shared-memory region
+  int hs_cap;         // doubles in that region (it doubles as the column staging ring of gram_P)
   LassoWs ws;
 };
 
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kMeta = 64;  // strong-set metadata staged per chunk
 constexpr int kHSlots = 148 * 4;  // Gram scratch slots (>= resident CTAs of the gram kernel)
-constexpr int kGramSmem = kMeta * 8 + 3 * kNX * 8 + 64 + kNX * 4;  // mg, gq, gq2, amat, gsh, ord
+constexpr int kGramSmem = kMeta * 8 + 3 * kNX * 8 + 64 + kNX * 4 - kNX * 8;  // mg, gq, gq2, amat, gsh, ord; as_ lives in global memory
 constexpr int kFixedSmem = 512 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4 + kMeta * (8 + 8 + 4 + 4) + 16;
 
 template <int T>
@@ -799,6 +804,227 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming helpers of the Gram kernel.  Design columns come out of L2 (~250 cycles unloaded, far
+// more under load); inside the big round kernel ptxas has no registers left to keep more than one
+// load per lane in flight, which leaves every streaming loop latency bound.  These are separate
+// functions (own register allocation) that issue a batch of kMLP 16-byte loads per lane before the
+// first use.  The per-lane accumulation order is exactly that of the plain loops they replace.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMLP = 8;
+
+__device__ __forceinline__ double2 ldg2_if(const double* p, bool ok) {
+  return ok ? ldg2(p) : make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ double2 lds2_if(const double* p, bool ok) {
+  return ok ? *reinterpret_cast<const double2*>(p) : make_double2(0.0, 0.0);
+}
+
+// sum_i a_i z_i : z a design column (global), a an n-vector (shared or global).  Every lane runs
+// the same number of batches (out-of-range slots load nothing and add an exact zero), so the whole
+// column costs ceil(ldx / (64 kMLP)) exposed L2 round trips.
+__device__ __noinline__ double wdot_a(const double* __restrict__ z, const double* a, int ldx) {
+  const int lane = threadIdx.x & 31;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = 2 * lane; i < ldx; i += 64 * kMLP) {
+    double2 zz[kMLP];
+#pragma unroll
+    for (int u = 0; u < kMLP; ++u) zz[u] = ldg2_if(z + i + 64 * u, i + 64 * u < ldx);
+#pragma unroll
+    for (int u = 0; u < kMLP; ++u) {
+      const double2 r = lds2_if(a + i + 64 * u, i + 64 * u < ldx);
+      s0 += r.x * zz[u].x;
+      s1 += r.y * zz[u].y;
+    }
+  }
+  return warp_sum(s0 + s1);
+}
+
+// (sum_i w_i z_i, sum_i r_i z_i)
+__device__ __noinline__ double2 wdot_wr(const double* __restrict__ z, const double* w,
+                                        const double* r, int ldx) {
+  const int lane = threadIdx.x & 31;
+  double pa = 0.0, pb = 0.0, ra = 0.0, rb = 0.0;
+  for (int i = 2 * lane; i < ldx; i += 64 * kMLP) {
+    double2 zz[kMLP];
+#pragma unroll
+    for (int u = 0; u < kMLP; ++u) zz[u] = ldg2_if(z + i + 64 * u, i + 64 * u < ldx);
+#pragma unroll
+    for (int u = 0; u < kMLP; ++u) {
+      const bool ok = i + 64 * u < ldx;
+      const double2 ww = lds2_if(w + i + 64 * u, ok);
+      const double2 rr = lds2_if(r + i + 64 * u, ok);
+      pa += ww.x * zz[u].x;
+      pb += ww.y * zz[u].y;
+      ra += rr.x * zz[u].x;
+      rb += rr.y * zz[u].y;
+    }
+  }
+  return make_double2(warp_sum(pa + pb), warp_sum(ra + rb));
+}
+
+// sum_i w_i x_i z_i : x the entering column (shared by all warps, L1), z a member column
+__device__ __noinline__ double wdot_wxz(const double* __restrict__ z, const double* __restrict__ x,
+                                        const double* w, int ldx) {
+  const int lane = threadIdx.x & 31;
+  double s0 = 0.0, s1 = 0.0;
+  constexpr int U = kMLP / 2;
+  for (int i = 2 * lane; i < ldx; i += 64 * U) {
+    double2 zz[U], xx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      zz[u] = ldg2_if(z + i + 64 * u, i + 64 * u < ldx);
+      xx[u] = ldg2_if(x + i + 64 * u, i + 64 * u < ldx);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double2 ww = lds2_if(w + i + 64 * u, i + 64 * u < ldx);
+      s0 += ww.x * xx[u].x * zz[u].x;
+      s1 += ww.y * xx[u].y * zz[u].y;
+    }
+  }
+  return warp_sum(s0 + s1);
+}
+
+// (s0, s1) += sum_l c_l * Xs[i .. i+1, k_l] for one row pair; zero coefficients add an exact zero
+__device__ __noinline__ double2 rows_comb(const double* __restrict__ Xi, size_t ldx, const int* ks,
+                                          const double* cs, int m, double s0, double s1) {
+  int l = 0;
+  for (; l + kMLP <= m; l += kMLP) {
+    double2 xx[kMLP];
+#pragma unroll
+    for (int u = 0; u < kMLP; ++u) xx[u] = ldg2(Xi + (size_t)ks[l + u] * ldx);
+#pragma unroll
+    for (int u = 0; u < kMLP; ++u) {
+      const double c = cs[l + u];
+      s0 += c * xx[u].x;
+      s1 += c * xx[u].y;
+    }
+  }
+  for (; l < m; ++l) {
+    const double c = cs[l];
+    const double2 x = ldg2(Xi + (size_t)ks[l] * ldx);
+    s0 += c * x.x;
+    s1 += c * x.y;
+  }
+  return make_double2(s0, s1);
+}
+
+// The same Gram block with the design columns staged through shared memory: 16-row slabs of the
+// m active columns are pulled in with cp.async by the whole CTA (every column read once per
+// pass instead of once per tile, NS slabs in flight, no registers tied up), the warps feed DMMA
+// from the slab.  Columns sit 128 bytes apart with the 16-byte chunks XOR-swizzled on the column
+// parity, so the four-lane k groups of two neighbouring columns hit different banks.  The ring
+// lives in the packed-Gram region, which is dead while the block is being rebuilt.  Summation
+// order per element is that of gram_P.  Returns false when the ring does not fit.
+template <int T>
+__device__ __noinline__ bool gram_P_slab_fn(const double* __restrict__ Xs, int ldx, const int* ia, int m,
+                                               const double* wv, double* Hsm, int hs_cap, double* H) {
+  {
+    constexpr int ldh = kNX;
+    const int tid = threadIdx.x;
+    constexpr int R = 16;
+    const int slab_d = m * R;
+    int ns = slab_d > 0 ? hs_cap / slab_d : 0;
+    if (ns < 2) return false;
+    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2, nslab = ldx / R;
+    const int nchunk = m * (R / 2);
+    auto issue = [&](int sl, int stage) {
+      double* dst = Hsm + stage * slab_d;
+      const double* src = Xs + (size_t)sl * R;
+      for (int c = tid; c < nchunk; c += T) {
+        const int cl = c >> 3, ch = c & 7;
+        cpa16(dst + cl * R + ((ch ^ ((cl & 1) << 2)) << 1), src + (size_t)ia[cl] * ldx + ch * 2);
+      }
+    };
+    auto run = [&](auto nsc) {
+      constexpr int NS = decltype(nsc)::value;
+      for (int t0 = 0; t0 < ntile; t0 += 2 * nw) {  // a pass: two tiles per warp
+        int cI[2][2], cJ[2][2], TI[2], TJ[2];
+        bool live[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int tix = t0 + warp + q * nw;
+          live[q] = tix < ntile;
+          int J = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+          while ((J + 1) * (J + 2) / 2 <= tix) ++J;
+          while (J * (J + 1) / 2 > tix) --J;
+          const int I = tix - J * (J + 1) / 2;
+          TI[q] = I; TJ[q] = J;
+          auto cl = [&](int idx) { return idx < m ? idx : m - 1; };
+          cI[q][0] = cl(I * 16 + g8); cI[q][1] = cl(I * 16 + 8 + g8);
+          cJ[q][0] = cl(J * 16 + g8); cJ[q][1] = cl(J * 16 + 8 + g8);
+        }
+        double acc[2][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[q][e] = 0.0;
+        __syncthreads();  // the ring is free (previous pass / previous user of the region)
+#pragma unroll
+        for (int sl = 0; sl < NS - 1; ++sl) {
+          if (sl < nslab) issue(sl, sl);
+          cpa_commit();
+        }
+        for (int sl = 0; sl < nslab; ++sl) {
+          cpa_wait<NS - 2>();
+          __syncthreads();  // slab sl has landed for everyone; slab sl-1 is fully consumed
+          if (sl + NS - 1 < nslab) issue(sl + NS - 1, (sl + NS - 1) % NS);
+          cpa_commit();
+          const double* st = Hsm + (sl % NS) * slab_d;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const double2 w = *reinterpret_cast<const double2*>(wv + sl * R + kk * 8 + 2 * t4);
+            const int ch = kk * 4 + t4;
+            auto ld = [&](int cl) {
+              return *reinterpret_cast<const double2*>(st + cl * R + ((ch ^ ((cl & 1) << 2)) << 1));
+            };
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (!live[q]) continue;
+              const double2 a0 = ld(cI[q][0]), a1 = ld(cI[q][1]);
+              double2 b0 = ld(cJ[q][0]), b1 = ld(cJ[q][1]);
+              b0.x *= w.x; b0.y *= w.y; b1.x *= w.x; b1.y *= w.y;
+              dmma(acc[q][0], acc[q][1], a0.x, b0.x);
+              dmma(acc[q][2], acc[q][3], a0.x, b1.x);
+              dmma(acc[q][4], acc[q][5], a1.x, b0.x);
+              dmma(acc[q][6], acc[q][7], a1.x, b1.x);
+              dmma(acc[q][0], acc[q][1], a0.y, b0.y);
+              dmma(acc[q][2], acc[q][3], a0.y, b1.y);
+              dmma(acc[q][4], acc[q][5], a1.y, b0.y);
+              dmma(acc[q][6], acc[q][7], a1.y, b1.y);
+            }
+          }
+        }
+        cpa_wait<0>();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (!live[q]) continue;
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int r = TI[q] * 16 + a * 8 + g8, cc = TJ[q] * 16 + b * 8 + 2 * t4 + e;
+                if (r < m && cc < m && (TI[q] != TJ[q] || r <= cc)) {
+                  const double v = acc[q][a * 4 + b * 2 + e];
+                  H[r + (size_t)cc * ldh] = v;
+                  H[cc + (size_t)r * ldh] = v;
+                }
+              }
+        }
+      }
+    };
+    if (ns >= 4) run(std::integral_constant<int, 4>());
+    else if (ns == 3) run(std::integral_constant<int, 3>());
+    else run(std::integral_constant<int, 2>());
+    __syncthreads();
+    return true;
+  }
+}
+
 // One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane).  The
 // Hessian column of step t+NB is pulled into L1 with prefetch.global.L1 while step t runs (no
 // registers are tied up, so nothing spills behind the load), the column of step t is then an L1
@@ -876,17 +1102,234 @@ __device__ __noinline__ void gram_sweep_warp(const double* H, int ldh, int m, bo
   }
 }
 
+// The same sweep with the Gram block in shared memory, packed lower-triangular by rows
+// (element (r, c), r >= c, at r(r+1)/2 + c).  Column l seen by lane j is the contiguous run
+// l(l+1)/2 + j for j <= l and the triangular-stride run j(j+1)/2 + l below it; triangular numbers
+// visit every residue mod 16 exactly twice per 32 lanes, so both halves are bank-conflict free.
+//
+// A sweep is one long dependent chain (step t needs q after step t-1), and the FP64 pipe it runs
+// on is shared with the DMMA / DFMA streams of the neighbouring warps, so the step is written to
+// keep that chain minimal: shuffle -> DFMA (u) -> DADD (|u| - lambda) -> soft threshold in integer
+// ALU ops on the sign word -> DMUL (new coefficient) -> select -> DADD (d) -> DFMA (q update).
+// Nothing branches on the chain (d = 0 makes every update an exact no-op), everything else of
+// step t+1 -- scalars, the Gram column, the index -- is loaded while step t's chain drains, and in
+// natural order the shuffle source register is static.  Same arithmetic, same results as
+// gram_sweep_warp.
+struct SweepAcc {
+  double dlx, q0;
+  unsigned dty, bad;
+};
+
+__device__ __forceinline__ double sweep_step(double ql, double v, double ak, double rv, double al,
+                                             double sw, SweepAcc& A, double& anew_out) {
+  const double u = fma(v, ak, ql);
+  const double r = fabs(u) - al;
+  // anew = r > 0 ? sign(r, u) * rv : 0 (glmnet), the sign transfer in integer ALU ops and the
+  // compare running beside the multiply instead of in front of it
+  const double cs = __hiloint2double((__double2hiint(r) & 0x7fffffff) | (__double2hiint(u) & 0x80000000),
+                                     __double2loint(r));
+  const double t = cs * rv;
+  const double anew = r > 0.0 ? t : 0.0;
+  const double d = anew - ak;
+  // off the chain
+  A.dlx = fmax(A.dlx, v * d * d);
+  A.q0 = fma(-d, sw, A.q0);
+  A.bad |= anew != anew;
+  A.dty |= (unsigned)(__double2hiint(d) << 1) | (unsigned)__double2loint(d);
+  anew_out = anew;
+  return d;
+}
+
+template <int Q, bool BYIDX>
+__device__ __noinline__ void gram_sweep_warp_sm(const double* Hp, int m, const int* ord, double* gq,
+                                                const double* va, const double* vinv, double* aact,
+                                                const double* swa, double al, double* gsh,
+                                                double dlx, double q0) {
+  const int lane = threadIdx.x & 31;
+  double qr[Q], hn[Q];
+  int tj[Q];
+#pragma unroll
+  for (int e = 0; e < Q; ++e) {
+    const int j = lane + 32 * e;
+    qr[e] = j < m ? gq[j] : 0.0;
+    tj[e] = j * (j + 1) / 2;
+  }
+  auto ldcol = [&](int l) {
+    const int tl = l * (l + 1) / 2;
+#pragma unroll
+    for (int e = 0; e < Q; ++e) {
+      const int j = lane + 32 * e;
+      hn[e] = j < m ? Hp[j <= l ? tl + j : tj[e] + l] : 0.0;
+    }
+  };
+  SweepAcc A = {dlx, q0, 0u, 0u};
+  int ln = BYIDX ? ord[0] : 0;
+  double vn = va[ln], an = aact[ln], sn = swa[ln], rn = vinv[ln];
+  ldcol(ln);
+  if (BYIDX) {
+    for (int t = 0; t < m; ++t) {
+      const int l = ln;
+      const double v = vn, ak = an, sw = sn, rv = rn;
+      double hc[Q];
+#pragma unroll
+      for (int e = 0; e < Q; ++e) hc[e] = hn[e];
+      if (t + 1 < m) {
+        ln = ord[t + 1];
+        vn = va[ln]; an = aact[ln]; sn = swa[ln]; rn = vinv[ln];
+        ldcol(ln);
+      }
+      double sel = qr[0];
+      const int qi = l >> 5;
+#pragma unroll
+      for (int e = 1; e < Q; ++e) sel = qi == e ? qr[e] : sel;
+      const double ql = __shfl_sync(0xffffffffu, sel, l & 31);
+      double anew;
+      const double d = sweep_step(ql, v, ak, rv, al, sw, A, anew);
+#pragma unroll
+      for (int e = 0; e < Q; ++e) qr[e] = fma(-d, hc[e], qr[e]);
+      if (lane == 0) aact[l] = anew;
+    }
+  } else {
+#pragma unroll
+    for (int e0 = 0; e0 < Q; ++e0) {
+      const int tend = m - 32 * e0 < 32 ? m - 32 * e0 : 32;
+      for (int tt = 0; tt < tend; ++tt) {
+        const int l = 32 * e0 + tt;
+        const double v = vn, ak = an, sw = sn, rv = rn;
+        double hc[Q];
+#pragma unroll
+        for (int e = 0; e < Q; ++e) hc[e] = hn[e];
+        if (l + 1 < m) {
+          ln = l + 1;
+          vn = va[ln]; an = aact[ln]; sn = swa[ln]; rn = vinv[ln];
+          ldcol(ln);
+        }
+        const double ql = __shfl_sync(0xffffffffu, qr[e0], tt);
+        double anew;
+        const double d = sweep_step(ql, v, ak, rv, al, sw, A, anew);
+#pragma unroll
+        for (int e = 0; e < Q; ++e) qr[e] = fma(-d, hc[e], qr[e]);
+        if (lane == 0) aact[l] = anew;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < Q; ++e) {
+    const int j = lane + 32 * e;
+    if (j < m) gq[j] = qr[e];
+  }
+  if (lane == 0) {
+    gsh[0] = A.bad ? NAN : A.dlx;
+    gsh[1] = A.q0;
+    gsh[2] = A.dty ? 1.0 : 0.0;
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void gram_sweep_sm(const double* Hp, int m, bool by_index, const int* ord,
+                                              double* gq, const double* va, const double* vinv,
+                                              double* aact, const double* swa, double al,
+                                              double* gsh, double dlx, double q0) {
+  if (by_index) gram_sweep_warp_sm<Q, true>(Hp, m, ord, gq, va, vinv, aact, swa, al, gsh, dlx, q0);
+  else gram_sweep_warp_sm<Q, false>(Hp, m, ord, gq, va, vinv, aact, swa, al, gsh, dlx, q0);
+}
+
+// The same step sequence with the Gram block in global memory (active sets too large for the
+// packed shared-memory copy): the column of step t is loaded at the top of the step and consumed
+// after the scalar chain, and pulled into L1 NB steps ahead with prefetch.global.L1 (one sector
+// per four lanes), so the load is an L1 hit hidden behind the chain.  Q up to 12 keeps active sets
+// of up to 384 variables in one warp's registers.
+template <int Q, bool BYIDX>
+__device__ __noinline__ void gram_sweep_warp_g(const double* __restrict__ H, int m, const int* ord,
+                                               double* gq, const double* va, const double* vinv,
+                                               double* aact, const double* swa, double al,
+                                               double* gsh, double dlx, double q0) {
+  constexpr int NB = 4, ldh = kNX;
+  const int lane = threadIdx.x & 31;
+  double qr[Q];
+#pragma unroll
+  for (int e = 0; e < Q; ++e) {
+    const int j = lane + 32 * e;
+    qr[e] = j < m ? gq[j] : 0.0;
+  }
+  auto pf = [&](int t) {
+    if (t < m && (lane & 3) == 0) {
+      const double* c = H + (size_t)(BYIDX ? ord[t] : t) * ldh + lane;
+#pragma unroll
+      for (int e = 0; e < Q; ++e)
+        if (lane + 32 * e < m) prefetch_l1(c + 32 * e);
+    }
+  };
+#pragma unroll
+  for (int b = 0; b < NB; ++b) pf(b);
+  SweepAcc A = {dlx, q0, 0u, 0u};
+  int ln = BYIDX ? ord[0] : 0;
+  double vn = va[ln], an = aact[ln], sn = swa[ln], rn = vinv[ln];
+  auto step = [&](int t, int l, double ql_src, int src_lane) {
+    const double v = vn, ak = an, sw = sn, rv = rn;
+    double hc[Q];
+    const double* c = H + (size_t)l * ldh + lane;
+#pragma unroll
+    for (int e = 0; e < Q; ++e) hc[e] = lane + 32 * e < m ? c[32 * e] : 0.0;
+    pf(t + NB);
+    if (t + 1 < m) {
+      ln = BYIDX ? ord[t + 1] : t + 1;
+      vn = va[ln]; an = aact[ln]; sn = swa[ln]; rn = vinv[ln];
+    }
+    const double ql = __shfl_sync(0xffffffffu, ql_src, src_lane);
+    double anew;
+    const double d = sweep_step(ql, v, ak, rv, al, sw, A, anew);
+#pragma unroll
+    for (int e = 0; e < Q; ++e) qr[e] = fma(-d, hc[e], qr[e]);
+    if (lane == 0) aact[l] = anew;
+  };
+  if (BYIDX) {
+    for (int t = 0; t < m; ++t) {
+      const int l = ln;
+      double sel = qr[0];
+      const int qi = l >> 5;
+#pragma unroll
+      for (int e = 1; e < Q; ++e) sel = qi == e ? qr[e] : sel;
+      step(t, l, sel, l & 31);
+    }
+  } else {
+#pragma unroll
+    for (int e0 = 0; e0 < Q; ++e0) {
+      const int tend = m - 32 * e0 < 32 ? m - 32 * e0 : 32;
+      for (int tt = 0; tt < tend; ++tt) step(32 * e0 + tt, 32 * e0 + tt, qr[e0], tt);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < Q; ++e) {
+    const int j = lane + 32 * e;
+    if (j < m) gq[j] = qr[e];
+  }
+  if (lane == 0) {
+    gsh[0] = A.bad ? NAN : A.dlx;
+    gsh[1] = A.q0;
+    gsh[2] = A.dty ? 1.0 : 0.0;
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void gram_sweep_g(const double* H, int m, bool by_index, const int* ord,
+                                             double* gq, const double* va, const double* vinv,
+                                             double* aact, const double* swa, double al, double* gsh,
+                                             double dlx, double q0) {
+  if (by_index) gram_sweep_warp_g<Q, true>(H, m, ord, gq, va, vinv, aact, swa, al, gsh, dlx, q0);
+  else gram_sweep_warp_g<Q, false>(H, m, ord, gq, va, vinv, aact, swa, al, gsh, dlx, q0);
+}
+
 // The Gram-space round kernel (default): same state machine and phase A as lasso_round_kernel,
 // phase B reformulated so that no coordinate update touches an n-long vector.
 template <int T, bool STAGED>
-__global__ void __launch_bounds__(T, (T <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(T, (T <= 128 ? 4 : T <= 256 ? 2 : 1))
 lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ nextlist,
                    int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* red = reinterpret_cast<double*>(smraw);
   double* aact = red + 512;
-  double* as_ = aact + kNX;
-  double* va = as_ + kNX;
+  double* va = aact + kNX;
   double* swa = va + kNX;
   double* xma = swa + kNX;
   double* xia = xma + kNX;
@@ -904,6 +1347,9 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   int* ord = reinterpret_cast<int*>(gsh + 8);              // active positions by variable index
   double* wv = reinterpret_cast<double*>(ord + kNX);
   double* wrv = wv + A.ldx;
+  double* Hsm = STAGED ? wrv + A.ldx : wv;                 // packed Gram block (A.mh rows at most)
+  const int mh = A.mh;
+  int hs_m = 0;  // rows of the shared-memory block that mirror H (usable by the sweep iff == m)
 
   const int tid = threadIdx.x;
   int phase = 0;
@@ -912,6 +1358,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // cycles: phaseA, vectors, gramP, sweeps, materialise, inactive, relin, irls count; [8] sweep steps [9] sweeps [10] inactive columns [11] checks [12] sum m at Gram build
   long long tmark = clock64();
   const bool timing = (A.prm.dbg & 128) != 0;
+  const bool mlp = (A.prm.dbg & 256) == 0;  // batched-load streaming helpers (bit 256: plain loops)
   auto lap = [&](int k) {
     if (timing) { const long long t = clock64(); tph[k] += t - tmark; tmark = t; }
   };
@@ -935,6 +1382,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   int* SIc = A.ws.SIDX + (size_t)pid * p_pad;
   int* IAg = A.ws.IA + (size_t)pid * kNX;
   double* AAg = A.ws.AACT + (size_t)pid * kNX;
+  double* as_ = A.ws.AS + (size_t)pid * kNX;  // coefficients at the start of the IRLS step (global)
   double* Wg = A.ws.W + (size_t)pid * ldx;
   double* WRg = A.ws.WR + (size_t)pid * ldx;
   const double* y = A.Yn + (size_t)g * n;
@@ -1122,18 +1570,26 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
     for (int l = l0 + warp; l < l1; l += nw) {
       const double* c = Xs + (size_t)ia[l] * ldx;
-      double pa = 0.0, pb = 0.0, ra = 0.0, rb = 0.0;
+      double ps, rs;
+      if (mlp) {
+        const double2 pr = wdot_wr(c, wv, wrv, ldx);
+        ps = pr.x;
+        rs = pr.y;
+      } else {
+        double pa = 0.0, pb = 0.0, ra = 0.0, rb = 0.0;
 #pragma unroll 4
-      for (int i = 2 * lane; i < ldx; i += 64) {
-        const double2 x = ldg2(c + i);
-        const double2 w = *reinterpret_cast<const double2*>(wv + i);
-        const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-        pa += w.x * x.x;
-        pb += w.y * x.y;
-        ra += r.x * x.x;
-        rb += r.y * x.y;
+        for (int i = 2 * lane; i < ldx; i += 64) {
+          const double2 x = ldg2(c + i);
+          const double2 w = *reinterpret_cast<const double2*>(wv + i);
+          const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+          pa += w.x * x.x;
+          pb += w.y * x.y;
+          ra += r.x * x.x;
+          rb += r.y * x.y;
+        }
+        ps = warp_sum(pa + pb);
+        rs = warp_sum(ra + rb);
       }
-      const double ps = warp_sum(pa + pb), rs = warp_sum(ra + rb);
       if (lane == 0) {
         if (with_p) swa[l] = ps;
         gq[l] = rs;
@@ -1186,14 +1642,24 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     gram_fma += (unsigned long long)ntile * 256ull * (unsigned)ldx;
     __syncthreads();
   };
+  auto gram_P_slab = [&](int m) -> bool {
+    if (!gram_P_slab_fn<T>(Xs, ldx, ia, m, wv, Hsm, A.hs_cap, H)) return false;
+    const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2;
+    gram_fma += (unsigned long long)ntile * 256ull * (unsigned)ldx;
+    return true;
+  };
   // per-fit standardisation of the raw moments: H and v (-> va) ...
   auto gram_finish_H = [&](int m) {
+    const bool pack = m <= mh;
     for (int idx = tid; idx < m * m; idx += T) {
       const int r = idx % m, c = idx / m;
       const double P = H[r + (size_t)c * ldh];
-      H[r + (size_t)c * ldh] =
+      const double hv =
           xia[r] * xia[c] * (P - xma[r] * swa[c] - xma[c] * swa[r] + xma[r] * xma[c] * v0);
+      H[r + (size_t)c * ldh] = hv;
+      if (pack && r >= c) Hsm[r * (r + 1) / 2 + c] = hv;
     }
+    hs_m = pack ? m : -1;
     __syncthreads();
     for (int l = tid; l < m; l += T) va[l] = H[l + (size_t)l * ldh];
     __syncthreads();
@@ -1212,8 +1678,22 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // steps ahead -- no block barrier inside the sweep.  Larger active sets use the block version.
   auto gsweep_warp = [&](bool by_index, int m, double& dlx) {
     if (tid < 32) {
-      if (m <= 128) gram_sweep_warp<4, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
-      else gram_sweep_warp<8, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      if (hs_m == m) {
+        if (m <= 32) gram_sweep_sm<1>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+        else if (m <= 64) gram_sweep_sm<2>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+        else if (m <= 96) gram_sweep_sm<3>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+        else if (m <= 128) gram_sweep_sm<4>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+        else if (m <= 192) gram_sweep_sm<6>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+        else gram_sweep_sm<8>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      } else if (A.prm.dbg & 1024) {  // the first Gram-space sweep (A/B reference)
+        if (m <= 128) gram_sweep_warp<4, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+        else gram_sweep_warp<8, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      } else if (m <= 64) gram_sweep_g<2>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      else if (m <= 128) gram_sweep_g<4>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      else if (m <= 192) gram_sweep_g<6>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      else if (m <= 256) gram_sweep_g<8>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      else if (m <= 320) gram_sweep_g<10>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
+      else gram_sweep_g<12>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
     }
     __syncthreads();
     dlx = gsh[0];
@@ -1275,7 +1755,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     if (m == 0) return;
     tph[8] += m;
     tph[9] += 1;
-    if (m <= 256) gsweep_warp(by_index, m, dlx);
+    if (timing && tid == 0) atomicAdd(A.ws.phasecyc + 16 + (m - 1) / 32, (unsigned long long)m);
+    if (m <= ((A.prm.dbg & 1024) ? 256 : 384)) gsweep_warp(by_index, m, dlx);
     else gsweep_block(by_index, m, dlx);
   };
   auto gintercept = [&](int m, double& dlx) {
@@ -1300,6 +1781,11 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     const double shift = (az - azmat) - sh[0];
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
       double s0 = shift, s1 = shift;
+      if (mlp) {
+        const double2 sc = rows_comb(Xs + i, ldx, ia, amat, m, s0, s1);
+        s0 = sc.x;
+        s1 = sc.y;
+      } else
 #pragma unroll 4
       for (int l = 0; l < m; ++l) {
         const double c = amat[l];
@@ -1354,34 +1840,44 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     q0 -= d * sw;
     ++nin;
     if (nin > nx) return false;  // pmax overflow, handled by the caller
+    const bool grow = hs_m == m && m + 1 <= mh;  // the packed block takes row m as well
+    double* hrow = Hsm + m * (m + 1) / 2;
     // new Gram column against the m current members: one warp per member, no block barrier
     {
       const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
       for (int l = warp; l < m; l += nw) {
         const double* c = Xs + (size_t)ia[l] * ldx;
-        double s0 = 0.0, s1 = 0.0;
+        double acc;
+        if (mlp) {
+          acc = wdot_wxz(c, col, wv, ldx);
+        } else {
+          double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
-        for (int i = 2 * lane; i < ldx; i += 64) {
-          const double2 x = ldg2(col + i);
-          const double2 z = ldg2(c + i);
-          const double2 w = *reinterpret_cast<const double2*>(wv + i);
-          s0 += w.x * x.x * z.x;
-          s1 += w.y * x.y * z.y;
+          for (int i = 2 * lane; i < ldx; i += 64) {
+            const double2 x = ldg2(col + i);
+            const double2 z = ldg2(c + i);
+            const double2 w = *reinterpret_cast<const double2*>(wv + i);
+            s0 += w.x * x.x * z.x;
+            s1 += w.y * x.y * z.y;
+          }
+          acc = warp_sum(s0 + s1);
         }
-        const double acc = warp_sum(s0 + s1);
         if (lane == 0) {
           const double pl = swa[l] / xia[l] + xma[l] * v0m;  // raw sum w Xs_l back from h0_l
           const double h = xia[l] * xi * (acc - xma[l] * d2[0] - xm * pl + xma[l] * xm * v0);
           H[l + (size_t)m * ldh] = h;
           H[m + (size_t)l * ldh] = h;
+          if (grow) hrow[l] = h;
           gq[l] -= d * h;
         }
       }
       ncols += m;
       __syncthreads();
     }
+    hs_m = grow ? m + 1 : -1;
     if (tid == 0) {
       H[m + (size_t)m * ldh] = v;
+      if (grow) hrow[m] = v;
       MMc[k] = nin;
       ia[m] = k;
       xma[m] = xm;
@@ -1429,15 +1925,20 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         for (int j = j0 + warp; j < cn; j += nw) {
           if (mpos[j] < 0) {
             const double* c = Xs + (size_t)mk[j] * ldx;
-            double s0 = 0.0, s1 = 0.0;
+            double acc;
+            if (mlp) {
+              acc = wdot_a(c, wrv, ldx);
+            } else {
+              double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
-            for (int i = 2 * lane; i < ldx; i += 64) {
-              const double2 x = ldg2(c + i);
-              const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-              s0 += r.x * x.x;
-              s1 += r.y * x.y;
+              for (int i = 2 * lane; i < ldx; i += 64) {
+                const double2 x = ldg2(c + i);
+                const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+                s0 += r.x * x.x;
+                s1 += r.y * x.y;
+              }
+              acc = warp_sum(s0 + s1);
             }
-            const double acc = warp_sum(s0 + s1);
             if (lane == 0) mg[j] = mxi[j] * (acc - mxm[j] * q0);
           }
         }
@@ -1520,7 +2021,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         gram_vectors(0, m, rebuild);
         lap(1);
         if (rebuild) {
-          gram_P(m);
+          if ((dbg & 512) || !gram_P_slab(m)) gram_P(m);
           gram_finish_H(m);
           v0m = v0;
           H_valid = true;
@@ -1564,7 +2065,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             // with the current weights (then it is one, and coordinate descent converges).
             materialise(m);
             gram_vectors(0, m, true);
-            gram_P(m);
+            if ((dbg & 512) || !gram_P_slab(m)) gram_P(m);
             gram_finish_H(m);
             v0m = v0;
             gram_finish_vec(m, true);
@@ -1595,6 +2096,11 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum w, sum t f, sum wr, held-out deviance
       for (int i = 2 * tid; i < ldx; i += 2 * T) {
         double f0 = c0, f1 = c0;
+        if (mlp) {
+          const double2 fc2 = rows_comb(Xs + i, ldx, ia, gq2, nin, f0, f1);
+          f0 = fc2.x;
+          f1 = fc2.y;
+        } else
 #pragma unroll 4
         for (int l = 0; l < nin; ++l) {
           const double b = gq2[l];
@@ -1924,7 +2430,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oWR = take((size_t)ldx * P_pad * 8), oG = take((size_t)p_pad * P_pad * 8),
                oXM = take((size_t)p_pad * P_pad * 8), oXI = take((size_t)p_pad * P_pad * 8),
                oMM = take((size_t)p_pad * P * 4), oSI = take((size_t)p_pad * P * 4),
-               oIA = take((size_t)kNX * P * 4), oAA = take((size_t)kNX * P * 8),
+               oIA = take((size_t)kNX * P * 4), oAA = take((size_t)kNX * P * 8), oAS = take((size_t)kNX * P * 8),
                oPR = take(sizeof(LassoProb) * (size_t)P), oLam = take((size_t)kNLam * B * 8),
                oNl = take((size_t)B * 4), oLf = take((size_t)B * 4), oGs = take((size_t)B * 4),
                oGm = take((size_t)B * 8), oA0 = take((size_t)kNLam * B * 8),
@@ -1933,7 +2439,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oCv = take((size_t)kNLam * kMaxFolds * B * 8), oL0 = take((size_t)P * 4),
                oL1 = take((size_t)P * 4), oCt = take(64), oCc = take(64),
                oIn = take((size_t)p_pad * P * 4), oHf = take((size_t)kHSlots * 4),
-               oHs = take((size_t)kHSlots * kNX * kNX * 8), oPh = take(128);
+               oHs = take((size_t)kHSlots * kNX * kNX * 8), oPh = take(512);
   cudaError_t e;
   if (off > ws.cap_bytes) {
     if (ws.base) {
@@ -1950,7 +2456,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   ws.R = (double*)(b + oR); ws.W = (double*)(b + oW); ws.WR = (double*)(b + oWR);
   ws.G = (double*)(b + oG); ws.XM = (double*)(b + oXM); ws.XI = (double*)(b + oXI);
   ws.MM = (int*)(b + oMM); ws.SIDX = (int*)(b + oSI); ws.IA = (int*)(b + oIA);
-  ws.AACT = (double*)(b + oAA); ws.prob = (LassoProb*)(b + oPR); ws.lam = (double*)(b + oLam);
+  ws.AACT = (double*)(b + oAA); ws.AS = (double*)(b + oAS); ws.prob = (LassoProb*)(b + oPR); ws.lam = (double*)(b + oLam);
   ws.nlam_g = (int*)(b + oNl); ws.Lfinal = (int*)(b + oLf); ws.gstat = (int*)(b + oGs);
   ws.gmean = (double*)(b + oGm); ws.a0p = (double*)(b + oA0); ws.devp = (double*)(b + oDv);
   ws.ninp = (int*)(b + oNi); ws.nlpp = (int*)(b + oNp); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
@@ -1971,7 +2477,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   if ((e = cudaMemsetAsync(ws.counters, 0, 64, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ws.colcount, 0, 64, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ws.hflags, 0, (size_t)kHSlots * 4, s)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(ws.phasecyc, 0, 128, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.phasecyc, 0, 512, s)) != cudaSuccess) return e;
   cudaEventRecord(ws.ev[0], s);
   // the padding columns of the GEMM panel must hold finite numbers
   if (P_pad > P &&
@@ -2003,13 +2509,33 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   const size_t smem = mode == 2 ? smem_x : mode == 1 ? smem_s : kFixedSmem;
   bool gram = prm.gram != 0;
   if (const char* e = getenv("SAVER_LASSO_GRAM")) gram = atoi(e) != 0;
-  const size_t smem_g = kFixedSmem + kGramSmem + (size_t)2 * ldx * 8;
-  const bool gram_staged = smem_g <= 227 * 1024;
   int T = ldx <= 2048 ? 128 : ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
   if (gram) T = ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
   if (gram) if (const char* e = getenv("SAVER_GRAM_THREADS")) T = atoi(e);
   if (const char* e = getenv("SAVER_LASSO_THREADS")) T = atoi(e);  // tuning experiments only
   if (T != 128 && T != 256 && T != 512 && T != 1024) return cudaErrorInvalidValue;
+  // Gram kernel shared-memory plan: fixed state, then (staged) W / WR, then the packed Gram block
+  // of the warp sweep in whatever is left of the CTA's share of the SM (two CTAs per SM up to 256
+  // threads, one above).
+  const size_t smem_g0 = kFixedSmem + kGramSmem, smem_gw = (size_t)2 * ldx * 8;
+  int ctas = T <= 128 ? 4 : T <= 256 ? 2 : 1;  // resident CTAs per SM the register cap allows
+  if (const char* e = getenv("SAVER_GRAM_CTAS")) { const int c = atoi(e); if (c >= 1 && c < ctas) ctas = c; }
+  size_t budget = (size_t)(228 * 1024 - ctas * 1024) / ctas / 16 * 16;
+  if (budget > 227 * 1024) budget = 227 * 1024;
+  bool gram_staged = smem_g0 + smem_gw <= budget;
+  if (const char* e = getenv("SAVER_GRAM_STAGED")) gram_staged = gram_staged && atoi(e) != 0;
+  if (!gram_staged && smem_g0 > budget) budget = 227 * 1024;
+  size_t smem_gram = smem_g0 + (gram_staged ? smem_gw : 0);
+  {
+    size_t hs = smem_gram < budget ? (budget - smem_gram) / 16 * 16 : 0;
+    if (const char* e = getenv("SAVER_GRAM_HS")) { const size_t cap = (size_t)atol(e); if (hs > cap) hs = cap / 16 * 16; }
+    int mh = 0;
+    while (mh < 256 && (size_t)(mh + 1) * (mh + 2) / 2 * 8 <= hs) ++mh;
+    A.mh = mh;
+    A.hs_cap = mh * (mh + 1) / 2;
+    smem_gram += (size_t)mh * (mh + 1) / 2 * 8;
+    smem_gram = (smem_gram + 15) / 16 * 16;
+  }
   int cur = 0;
   cudaEventRecord(ws.ev[1], s);
   if ((e = cudaMemcpyAsync(ws.h_counter, ws.counters, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -2018,6 +2544,34 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     float ms = 0;
     cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]);
     ws.ms_setup += ms;
+  }
+  // The round kernels stream the design columns over and over while ~1 GB of per-problem panels
+  // (gradients, moments, working weights) passes through L2 once per round: keep the design in the
+  // persisting carve-out of L2 so that traffic does not evict it (hit rate of the column reads).
+  bool l2_window = false;
+  {
+    int dev = 0, max_persist = 0, max_window = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    bool want = true;
+    if (const char* e = getenv("SAVER_L2_PERSIST")) want = atoi(e) != 0;
+    if (want && max_persist > 0 && max_window > 0) {
+      size_t bytes = (size_t)ldx * D.p * sizeof(double);
+      if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = const_cast<double*>(D.Xs);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        const double ratio = (double)max_persist / (double)bytes;
+        attr.accessPolicyWindow.hitRatio = ratio < 1.0 ? (float)ratio : 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        l2_window = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+      }
+      cudaGetLastError();  // an unsupported attribute must not poison the launch checks below
+    }
   }
   bool gemm_pending = false;
   int live = ws.h_counter[0];
@@ -2030,7 +2584,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
     cudaEventRecord(ws.ev[0], s);
     if (gram) {
-      const size_t sm = gram_staged ? smem_g : kFixedSmem + kGramSmem;
+      const size_t sm = smem_gram;
       switch (T) {
         case 128: e = launch_gram_t<128>(A, list, next, cnt, live, gram_staged, sm, s); break;
         case 256: e = launch_gram_t<256>(A, list, next, cnt, live, gram_staged, sm, s); break;
@@ -2077,11 +2631,18 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     ws.cols_streamed += cc[0];
     ws.gram_fma += cc[4];
-    unsigned long long ph[16];
-    if ((e = cudaMemcpy(ph, ws.phasecyc, 128, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
-    for (int k = 0; k < 16; ++k) ws.phase_cycles[k] += ph[k];
+    unsigned long long ph[48];
+    if ((e = cudaMemcpy(ph, ws.phasecyc, 48 * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    for (int k = 0; k < 48; ++k) ws.phase_cycles[k] += ph[k];
     ws.cta_cycles += cc[1];
     if (cc[2] > ws.max_cta_cycles) ws.max_cta_cycles = cc[2];
+  }
+  if (l2_window) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
   }
   FinalArgs F;
   F.R = A; F.lmin_user = lmin_user; F.MU = MU; F.out4 = out4; F.status = status; F.stats = stats;

@@ -61,6 +61,7 @@ struct LassoWs {
   int *MM, *SIDX;            // p_pad x P: 0 none, -1 strong only, >0 active position / strong list
   int *IA;                   // kNX x P ever-active variables in order of entry
   double *AACT;              // kNX x P coefficients in active-list order (standardised scale)
+  double *AS;                // kNX x P coefficients at the start of the current IRLS step (gram kernel)
   LassoProb* prob;           // P
   double *lam;               // kNLam x B
   int *nlam_g, *Lfinal, *gstat;   // B
@@ -76,12 +77,12 @@ struct LassoWs {
   int *INACT;                // p_pad x P: inactive members of the strong set (gram kernel)
   int *hflags;               // Gram scratch slot flags
   double *Hs;                // Gram scratch: kHSlots x kNX x kNX
-  unsigned long long* phasecyc;  // [8] per-phase SM cycles of the gram kernel (bring-up / profiles)
+  unsigned long long* phasecyc;  // [48] per-phase SM cycles of the gram kernel (bring-up / profiles)
   // accounting (host side, cumulative over the handle's life)
   double ms_round = 0, ms_gemm = 0, ms_setup = 0;
   unsigned long long cols_streamed = 0, cta_cycles = 0, max_cta_cycles = 0, gram_fma = 0;
   long long rounds = 0;
-  unsigned long long phase_cycles[16] = {0};
+  unsigned long long phase_cycles[48] = {0};  // [16..35]: sweep steps by active-set size / 32
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void release();
 };

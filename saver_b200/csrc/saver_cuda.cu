@@ -59,6 +59,7 @@ int saver_cuda_destroy(saver_cuda_handle h) {
   cudaStreamSynchronize(h->stream);
   h->design.release();
   h->lasso.release();
+  cudaFree(h->csc_indptr); cudaFree(h->csc_indices); cudaFree(h->csc_data); cudaFree(h->csc_map);
   cudaStreamDestroy(h->stream);
   delete h;
   return SAVER_OK;
@@ -423,6 +424,12 @@ int saver_cuda_counters(saver_cuda_handle h, double* out8) {
 int saver_cuda_phase_cycles(saver_cuda_handle h, double* out8) {
   if (!h || !out8) return SAVER_ERR_ARG;
   for (int k = 0; k < 16; ++k) out8[k] = (double)h->lasso.phase_cycles[k];
+  return SAVER_OK;
+}
+
+int saver_cuda_sweep_hist(saver_cuda_handle h, double* out20) {
+  if (!h || !out20) return SAVER_ERR_ARG;
+  for (int k = 0; k < 20; ++k) out20[k] = (double)h->lasso.phase_cycles[16 + k];
   return SAVER_OK;
 }
 

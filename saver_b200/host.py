@@ -173,6 +173,11 @@ class CudaBackend:
     def set_design(self, xest):
         ops.set_design(xest, handle=self.handle)
 
+    def load_counts(self, x):
+        """Sparse input (R: dgCMatrix): upload once, keep resident (saver_cuda_set_counts_csc)."""
+        ops.set_counts_csc(x, handle=self.handle)
+        return DeviceCounts(x, self.handle)
+
     def calc_estimate(self, x, sf, scale_sf, mode, cutoff=0.0, coefs=None, self_col=None,
                       is_pred=None, pred_mask=None, foldid=None, nfolds=5, calc_maxcor=False,
                       estimates_only=False, want_mu=False, dfmax=300, nlambda=100, thresh=1e-7):
@@ -183,6 +188,16 @@ class CudaBackend:
                                  foldid=foldid, nfolds=nfolds, calc_maxcor=calc_maxcor,
                                  want_se=not estimates_only, want_mu=want_mu, dfmax=dfmax,
                                  nlambda=nlambda, thresh=thresh, handle=self.handle)
+
+
+class _Sums:
+    """Row / column sums of a DeviceCounts behind the ``x.sum(axis)`` the utils use."""
+
+    def __init__(self, dc):
+        self.dc, self.shape = dc, dc.shape
+
+    def sum(self, axis):
+        return self.dc.col_sums if axis == 0 else self.dc.row_sums
 
 
 class SaverResult:
@@ -197,7 +212,27 @@ class SaverResult:
         self.cell_names = cell_names
 
 
-def _dense_rows(x, rows):
+class DeviceCounts:
+    """A sparse count matrix resident on the device (csrc/sparse.cu).  Replaces the Matrix-package
+    calls of the reference's sparse path: colSums/rowSums (R/utils.R:72,100-115, R/saver.R:156),
+    as.matrix(x[block, ]) (R/calc_estimate.R:69) and the dense x.est (R/saver.R:157)."""
+
+    def __init__(self, x, handle):
+        self.shape = x.shape
+        self.handle = handle
+        self.col_sums, self.row_sums = ops.csc_sums(handle=handle)
+
+    def rows(self, rows):
+        return ops.csc_gather(rows, handle=self.handle)
+
+    def log_rows(self, rows, sf):
+        """log((x[rows, ] + 1) / sf), left on the device for saver_cuda_set_design."""
+        return ops.csc_gather(rows, sf=sf, transform=True, device=True, handle=self.handle)
+
+
+def _dense_rows(x, rows, dc=None):
+    if dc is not None:
+        return dc.rows(rows)
     if hasattr(x, "tocsc"):
         return np.asarray(x.tocsr()[rows].todense(), dtype=np.float64)
     return np.ascontiguousarray(x[rows], dtype=np.float64)
@@ -206,8 +241,9 @@ def _dense_rows(x, rows):
 class _Fit:
     """State shared by the stages of saver.fit (est / se / info assembly, R/saver_fit.R:60-70)."""
 
-    def __init__(self, x, sf, scale_sf, ngenes, ncells, estimates_only, backend, keep_mu, comm):
-        self.x, self.sf, self.scale_sf = x, sf, scale_sf
+    def __init__(self, x, sf, scale_sf, ngenes, ncells, estimates_only, backend, keep_mu, comm,
+                 dc=None):
+        self.x, self.sf, self.scale_sf, self.dc = x, sf, scale_sf, dc
         self.backend, self.comm = backend, comm
         self.estimates_only = estimates_only
         self.est = np.zeros((ngenes, ncells))
@@ -247,7 +283,7 @@ class _Fit:
         for b0 in range(0, mine.size, blk):
             p = mine[b0:b0 + blk]
             g = ind[p]
-            xb = _dense_rows(self.x, g)
+            xb = _dense_rows(self.x, g, self.dc)
             fold = None
             if mode == 1:
                 # seed j = 1-based position of the gene inside the stage block (R/calc_estimate.R:98)
@@ -292,7 +328,8 @@ class _Fit:
 def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, null_model,
               ngenes=None, ncells=None, gene_names=None, cell_names=None, estimates_only=False,
               *, self_col=None, backend=None, comm=None, perm="identity", fold_seed=0,
-              fold_method="philox", nfolds=5, keep_mu=False, messages=None, gather=True):
+              fold_method="philox", nfolds=5, keep_mu=False, messages=None, gather=True,
+              counts=None):
     """saver.fit (R/saver_fit.R:56-463): the stage schedule.
 
     x (genes x cells counts), x_est ((p, n) = t(x.est) of R/saver.R:157, gene-major),
@@ -306,17 +343,21 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
     ncells = x.shape[1] if ncells is None else ncells
     backend = backend or CudaBackend(comm=comm)
     nworkers = max(int(ncores), 1)
-    fit = _Fit(x, sf, scale_sf, ngenes, ncells, estimates_only, backend, keep_mu, comm)
+    fit = _Fit(x, sf, scale_sf, ngenes, ncells, estimates_only, backend, keep_mu, comm, counts)
     info = fit.info
     msg("Running SAVER with %d worker(s)" % nworkers)
     pred_genes = np.asarray(pred_genes, dtype=np.int64)
-    rs = np.asarray(x[pred_genes].sum(1)).ravel() if pred_genes.size else np.zeros(0)
+    if counts is not None:
+        rs = counts.row_sums[pred_genes]
+    else:
+        rs = np.asarray(x[pred_genes].sum(1)).ravel() if pred_genes.size else np.zeros(0)
     pred1 = pred_genes[rs > 0]
     npred = pred_genes.size
     if not null_model:
         msg("Calculating predictions for %d genes using %d genes and %d cells..."
             % (npred, x_est.shape[0], x_est.shape[1]))
-        if comm is not None and comm.world > 1 and comm.backend == "nccl":
+        if comm is not None and comm.world > 1 and comm.backend == "nccl" \
+                and isinstance(x_est, np.ndarray):
             # the design is uploaded once by rank 0 and broadcast over NVLink (NCCL)
             backend.set_design(comm.broadcast_array(x_est if comm.rank == 0 else None,
                                                     keep_on_device=True))
@@ -409,7 +450,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
     return finish(npred)
 
 
-def _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, block):
+def _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, block, dc=None):
     """Shared body of saver.fit.mean / saver.fit.null: calc.post on a supplied prediction."""
     ngenes, ncells = x.shape
     est = np.zeros((ngenes, ncells))
@@ -422,7 +463,7 @@ def _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, block
     h = backend.handle
     for b0 in range(0, ngenes, block):
         rows = np.arange(b0, min(ngenes, b0 + block))
-        xb = _dense_rows(x, rows)
+        xb = _dense_rows(x, rows, dc)
         t0 = time.time()
         r = ops.calc_post(xb, mu_rows(rows, xb), sf, scale_sf, want_se=not estimates_only,
                           want_info=False, handle=h)
@@ -434,7 +475,8 @@ def _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, block
     return dict(estimate=est, se=se, info=info, mu=None, status=np.zeros(ngenes, dtype=np.int32))
 
 
-def saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only=False, backend=None, comm=None):
+def saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only=False, backend=None, comm=None,
+                   counts=None):
     """saver.fit.mean (R/saver_fit.R:467-538) + calc.estimate.mean (R/calc_estimate.R:166-221):
     the user's mu, rescaled per gene to the mean of y, zero rows patched with the gene mean."""
     backend = backend or CudaBackend(comm=comm)
@@ -446,14 +488,16 @@ def saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only=False, backend=No
         imu[mm == 0] = gm[mm == 0][:, None]
         return imu * (y.mean(1) / imu.mean(1))[:, None]
 
-    return _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, backend.block)
+    return _fit_given_mu(x, sf, scale_sf, mu_rows, estimates_only, backend, comm, backend.block,
+                         counts)
 
 
-def saver_fit_null(x, ncores, sf, scale_sf, estimates_only=False, backend=None, comm=None):
+def saver_fit_null(x, ncores, sf, scale_sf, estimates_only=False, backend=None, comm=None,
+                   counts=None):
     """saver.fit.null (R/saver_fit.R:542-628) + calc.estimate.null (R/calc_estimate.R:226-277)."""
     backend = backend or CudaBackend(comm=comm)
     return _fit_given_mu(x, sf, scale_sf, lambda rows, xb: (xb / sf).mean(1), estimates_only,
-                         backend, comm, backend.block)
+                         backend, comm, backend.block, counts)
 
 
 def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=None,
@@ -476,31 +520,40 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
     if gene_names is None:
         gene_names = np.arange(1, ngenes + 1)
     msg("%d genes, %d cells" % (ngenes, ncells))
-    sf, scale_sf = calc_size_factor(x, size_factor, ncells)
     backend = backend or CudaBackend(comm=comm)
+    # sparse input stays sparse on the device; blocks are densified there (csrc/sparse.cu)
+    dc = backend.load_counts(x) if hasattr(x, "tocsc") and hasattr(backend, "load_counts") else None
+    sf, scale_sf = calc_size_factor(x if dc is None else _Sums(dc), size_factor, ncells)
     if mu is not None:
-        out = saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only, backend, comm)
+        out = saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only, backend, comm, dc)
     elif null_model:
-        out = saver_fit_null(x, ncores, sf, scale_sf, estimates_only, backend, comm)
+        out = saver_fit_null(x, ncores, sf, scale_sf, estimates_only, backend, comm, dc)
     else:
         pc = get_pred_cells(pred_cells, ncells)
-        pg = get_pred_genes(x, pred_genes, npred, ngenes)
-        rm = np.asarray(x.mean(1)).ravel()
+        pg = get_pred_genes(x if dc is None else _Sums(dc), pred_genes, npred, ngenes)
+        rm = np.asarray(x.mean(1)).ravel() if dc is None else dc.row_sums / ncells
         good = np.where(rm >= 0.1)[0]
         # x.est = t(log((x[good, ] + 1) / sf))  (R/saver.R:156-157), kept gene-major: (p, n)
-        x_est = np.log((_dense_rows(x, good) + 1.0) / sf)
+        if dc is not None:
+            x_est = dc.log_rows(good, sf)
+        else:
+            x_est = np.log((_dense_rows(x, good) + 1.0) / sf)
         # the x.est column carrying each gene's own name (R/calc_estimate.R:103), -1 if none
         self_col = np.full(ngenes, -1, dtype=np.int32)
         self_col[good] = np.arange(good.size, dtype=np.int32)
         if pred_genes_only:
-            x = x[pg]
+            if dc is not None:       # row subset of a resident sparse matrix: re-upload the slice
+                x = x.tocsr()[pg].tocsc()
+                dc = backend.load_counts(x)
+            else:
+                x = x[pg]
             gene_names = np.asarray(gene_names)[pg]
             self_col = self_col[pg]
             pg = np.arange(x.shape[0])
         out = saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pg, pc, null_model,
                         estimates_only=estimates_only, self_col=self_col, backend=backend,
                         comm=comm, perm=perm, fold_seed=fold_seed, fold_method=fold_method,
-                        nfolds=nfolds, keep_mu=return_mu, messages=msg)
+                        nfolds=nfolds, keep_mu=return_mu, messages=msg, counts=dc)
     msg("Done!")
     res = SaverResult(out["estimate"], out["se"], out["info"], out.get("mu"), gene_names,
                       cell_names)

@@ -273,3 +273,40 @@ def cor_adjust(est, se, by_cells=False, cor_in=None, col0=0, ncols=None, handle=
     h.check(h.lib.saver_cuda_cor_adjust(h.h, ptr(est), ptr(se), n, G, int(bool(by_cells)),
                                         ptr(cor_in), int(col0), int(ncols), ptr(out), int(dev)))
     return out
+
+
+def set_counts_csc(x, handle=None):
+    """Upload a scipy.sparse genes x cells matrix (kept resident; R's dgCMatrix layout)."""
+    h = handle or default_handle()
+    x = x.tocsc()
+    indptr = np.ascontiguousarray(x.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(x.indices, dtype=np.int32)
+    data = np.ascontiguousarray(x.data, dtype=np.float64)
+    G, n = x.shape
+    h.check(h.lib.saver_cuda_set_counts_csc(h.h, ptr(indptr), ptr(indices), ptr(data), G, n))
+    h.csc_shape = (G, n)
+
+
+def csc_sums(handle=None):
+    h = handle or default_handle()
+    G, n = h.csc_shape
+    cs, rs = np.zeros(n), np.zeros(G)
+    h.check(h.lib.saver_cuda_csc_sums(h.h, ptr(cs), ptr(rs)))
+    return cs, rs
+
+
+def csc_gather(gene_idx, sf=None, transform=False, device=False, handle=None):
+    """Dense (B, n) block of the resident sparse counts; log((x + 1) / sf) when transform."""
+    h = handle or default_handle()
+    G, n = h.csc_shape
+    idx = np.ascontiguousarray(gene_idx, dtype=np.int32)
+    B = idx.size
+    sfv = None if sf is None else _f64(sf)
+    if device:
+        import torch
+        out = torch.empty((B, n), dtype=torch.float64, device=torch.device("cuda", h.device))
+    else:
+        out = np.empty((B, n))
+    h.check(h.lib.saver_cuda_csc_gather(h.h, ptr(idx), B, ptr(sfv), int(bool(transform)), ptr(out),
+                                        int(bool(device))))
+    return out

@@ -33,6 +33,8 @@ for it in range(2):
         print('  steps/IRLS %.0f sweeps/IRLS %.1f cyc/step %.0f | inactive cols/IRLS %.0f checks/IRLS %.2f cyc/col %.0f | mean m %.0f' % (d_ph[8]/d_ph[7], d_ph[9]/d_ph[7], d_ph[3]/max(d_ph[8],1), d_ph[10]/d_ph[7], d_ph[11]/d_ph[7], d_ph[5]/max(d_ph[10],1), d_ph[12]/d_ph[7]))
         print('  activations/IRLS %.2f cyc/activation %.0f (%.1f%% of total)' % (d_ph[14]/d_ph[7], d_ph[13]/max(d_ph[14],1), 100*d_ph[13]/(tot+d_ph[13])), 'first part cyc %.0f' % (d_ph[15]/max(d_ph[14],1)))
     ph_prev = ph
+    hist = np.zeros(20); h.lib.saver_cuda_sweep_hist(h.h, ops.ptr(hist))
+    if hist.sum() > 0: print('  sweep steps by m/32: ' + ' '.join('%.1f' % (100 * v / hist.sum()) for v in hist))
     print('  gram TFLOP %.3g ;' % (2 * (e1[2] - e0[2]) / 1e12), end='')
     print('  cycles/pass (CTA lifetime) %.0f ; slot utilisation (2 CTA/SM) %.2f ; passes/gene %.3g ; sweeps/gene %.0f lmu mean %.1f' % (
         cyc / d[4], cyc / (d[0] * 1.965e6 * 296), d[4] / G, r['stats'][:, 2].mean(), r['stats'][:, 0].mean()))

@@ -1,0 +1,78 @@
+"""Sparse input (R: dgCMatrix): the resident CSC matrix and its device-side
+densification against scipy, and saver(sparse) against saver(dense) -- bit for bit, since both
+feed the same count panels to the same kernels (R/saver.R:156-157, R/calc_estimate.R:69)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import saver_b200
+from saver_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _counts(G, n, seed, density=0.15):
+    rng = np.random.default_rng(seed)
+    x = rng.poisson(2.0, (G, n)).astype(np.float64) * (rng.random((G, n)) < density)
+    x[3] = 0                      # an all-zero gene
+    x[5, ::7] = 0.0004            # below clean.data's 0.001 threshold -> treated as zero
+    return x
+
+
+@pytest.mark.parametrize("G,n", [(64, 33), (257, 1000), (40, 9001)])
+def test_csc_sums_and_gather_match_scipy(handle, G, n):
+    x = _counts(G, n, G + n)
+    ops.set_counts_csc(sp.csc_matrix(x), handle=handle)
+    xc = np.where(x < 0.001, 0.0, x)
+    cs, rs = ops.csc_sums(handle=handle)
+    assert np.array_equal(cs, xc.sum(0)) and np.array_equal(rs, xc.sum(1))
+    idx = np.array([G - 1, 3, 5, 0, 17], dtype=np.int32)
+    assert np.array_equal(ops.csc_gather(idx, handle=handle), xc[idx])
+    sf = np.random.default_rng(1).uniform(0.3, 3.0, n)
+    want = np.log((xc[idx] + 1.0) / sf)
+    got = ops.csc_gather(idx, sf=sf, transform=True, handle=handle)
+    assert np.allclose(got, want, rtol=1e-15, atol=1e-15)
+    dev = ops.csc_gather(idx, sf=sf, transform=True, device=True, handle=handle)
+    assert np.array_equal(dev.cpu().numpy(), got)
+    assert ops.csc_gather(np.zeros(0, dtype=np.int32), handle=handle).shape == (0, n)
+
+
+def test_csc_argument_errors(handle):
+    x = sp.csc_matrix(_counts(20, 12, 0))
+    ops.set_counts_csc(x, handle=handle)
+    with pytest.raises(saver_b200.SaverCudaError):
+        ops.csc_gather(np.array([20], dtype=np.int32), handle=handle)
+    with pytest.raises(saver_b200.SaverCudaError):
+        ops.csc_gather(np.array([-1], dtype=np.int32), handle=handle)
+
+
+def test_empty_matrix_has_zero_sums(handle):
+    ops.set_counts_csc(sp.csc_matrix((6, 9)), handle=handle)
+    cs, rs = ops.csc_sums(handle=handle)
+    assert not cs.any() and not rs.any()
+    assert not ops.csc_gather(np.arange(6, dtype=np.int32), handle=handle).any()
+
+
+@pytest.mark.parametrize("kw", [dict(do_fast=False), dict(do_fast=True, perm=3),
+                                dict(null_model=True), dict(do_fast=False, size_factor=1),
+                                dict(do_fast=False, pred_genes=np.array([2, 9, 30]),
+                                     pred_genes_only=True)])
+def test_saver_sparse_equals_dense(kw):
+    x = synth.nb_counts(150, 90, seed=2).astype(np.float64)
+    x[:, 11] = 0                                   # an empty cell: dropped by clean.data
+    a = saver_b200.saver(x, fold_seed=5, **kw)
+    b = saver_b200.saver(sp.csr_matrix(x), fold_seed=5, **kw)
+    # the counts panels are identical; the design differs by the ulp between the device's log and
+    # numpy's, which the 3-decimal rounding of the prediction absorbs (R/expr_predict.R:58,80)
+    assert np.allclose(a.estimate, b.estimate, rtol=1e-9) and np.allclose(a.se, b.se, rtol=1e-9)
+    assert np.array_equal(a.info["size.factor"], b.info["size.factor"])
+    for k in ("maxcor", "lambda.max", "lambda.min", "sd.cv"):
+        assert np.allclose(a.info[k], b.info[k], rtol=1e-9, equal_nan=True), k
+
+
+def test_saver_sparse_with_mu(handle):
+    x = synth.nb_counts(60, 50, seed=4).astype(np.float64)
+    mu = np.random.default_rng(0).gamma(2.0, 1.0, x.shape)
+    a = saver_b200.saver(x, mu=mu)
+    b = saver_b200.saver(sp.csc_matrix(x), mu=mu)
+    assert np.array_equal(a.estimate, b.estimate) and np.array_equal(a.se, b.se)
