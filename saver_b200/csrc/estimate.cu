@@ -283,7 +283,7 @@ extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, in
         prm.alf_wide = prm.alf_tall = 1.0;
       }
       CU(cudaGetLastError());
-      const int chunk = lasso_max_block(prm.NF);
+      const int chunk = lasso_max_block(prm.NF, D);
       for (int b0 = 0; b0 < Bp; b0 += chunk) {
         prm.B = Bp - b0 < chunk ? Bp - b0 : chunk;
         CU(lasso_run(D, h->lasso, prm, Yp.p + n * b0, dFoldP.p + n * b0, dSelfP.p + b0,

@@ -61,7 +61,6 @@ struct RoundArgs {
   const int* fold;    // n x B: 0 = not a pred cell, 1..nfolds (path variant: any non-zero)
   const int* self;    // B or null
   int mh;             // largest active set whose packed Gram block fits the shared-memory region
-  int hs_cap;         // doubles in that region (it doubles as the column staging ring of gram_P)
   LassoWs ws;
 };
 
@@ -886,6 +885,106 @@ __device__ __noinline__ double wdot_wxz(const double* __restrict__ z, const doub
   return warp_sum(s0 + s1);
 }
 
+// Four columns per call: the loads of all four are in flight together (4 x kMLP4 16-byte loads per
+// lane) and the shared-memory operand is read once.  Per-column accumulation order is unchanged.
+constexpr int kMLP4 = 4;
+
+// out[c] = sum_i a_i z_c,i
+__device__ __noinline__ void wdot_a4(const double* __restrict__ z0, const double* __restrict__ z1,
+                                     const double* __restrict__ z2, const double* __restrict__ z3,
+                                     const double* a, int ldx, double* out) {
+  const int lane = threadIdx.x & 31;
+  const double* zp[4] = {z0, z1, z2, z3};
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  for (int i = 2 * lane; i < ldx; i += 64 * kMLP4) {
+    double2 zz[4][kMLP4];
+#pragma unroll
+    for (int u = 0; u < kMLP4; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zz[c][u] = ldg2_if(zp[c] + i + 64 * u, i + 64 * u < ldx);
+#pragma unroll
+    for (int u = 0; u < kMLP4; ++u) {
+      const double2 r = lds2_if(a + i + 64 * u, i + 64 * u < ldx);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        s0[c] += r.x * zz[c][u].x;
+        s1[c] += r.y * zz[c][u].y;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = warp_sum(s0[c] + s1[c]);
+}
+
+// out[c] = sum_i w_i x_i z_c,i
+__device__ __noinline__ void wdot_wxz4(const double* __restrict__ z0, const double* __restrict__ z1,
+                                       const double* __restrict__ z2, const double* __restrict__ z3,
+                                       const double* __restrict__ x, const double* w, int ldx,
+                                       double* out) {
+  const int lane = threadIdx.x & 31;
+  const double* zp[4] = {z0, z1, z2, z3};
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  constexpr int U = 3;
+  for (int i = 2 * lane; i < ldx; i += 64 * U) {
+    double2 zz[4][U], xx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = i + 64 * u < ldx;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zz[c][u] = ldg2_if(zp[c] + i + 64 * u, ok);
+      xx[u] = ldg2_if(x + i + 64 * u, ok);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double2 ww = lds2_if(w + i + 64 * u, i + 64 * u < ldx);
+      const double wx0 = ww.x * xx[u].x, wx1 = ww.y * xx[u].y;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        s0[c] += wx0 * zz[c][u].x;
+        s1[c] += wx1 * zz[c][u].y;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = warp_sum(s0[c] + s1[c]);
+}
+
+// (pout[c], rout[c]) = (sum_i w_i z_c,i, sum_i r_i z_c,i)
+__device__ __noinline__ void wdot_wr4(const double* __restrict__ z0, const double* __restrict__ z1,
+                                      const double* __restrict__ z2, const double* __restrict__ z3,
+                                      const double* w, const double* r, int ldx, double* pout,
+                                      double* rout) {
+  const int lane = threadIdx.x & 31;
+  const double* zp[4] = {z0, z1, z2, z3};
+  double pa[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0}, ra[4] = {0, 0, 0, 0}, rb[4] = {0, 0, 0, 0};
+  constexpr int U = 3;
+  for (int i = 2 * lane; i < ldx; i += 64 * U) {
+    double2 zz[4][U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zz[c][u] = ldg2_if(zp[c] + i + 64 * u, i + 64 * u < ldx);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = i + 64 * u < ldx;
+      const double2 ww = lds2_if(w + i + 64 * u, ok);
+      const double2 rr = lds2_if(r + i + 64 * u, ok);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        pa[c] += ww.x * zz[c][u].x;
+        pb[c] += ww.y * zz[c][u].y;
+        ra[c] += rr.x * zz[c][u].x;
+        rb[c] += rr.y * zz[c][u].y;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    pout[c] = warp_sum(pa[c] + pb[c]);
+    rout[c] = warp_sum(ra[c] + rb[c]);
+  }
+}
+
 // (s0, s1) += sum_l c_l * Xs[i .. i+1, k_l] for one row pair; zero coefficients add an exact zero
 __device__ __noinline__ double2 rows_comb(const double* __restrict__ Xi, size_t ldx, const int* ks,
                                           const double* cs, int m, double s0, double s1) {
@@ -908,121 +1007,6 @@ __device__ __noinline__ double2 rows_comb(const double* __restrict__ Xi, size_t 
     s1 += c * x.y;
   }
   return make_double2(s0, s1);
-}
-
-// The same Gram block with the design columns staged through shared memory: 16-row slabs of the
-// m active columns are pulled in with cp.async by the whole CTA (every column read once per
-// pass instead of once per tile, NS slabs in flight, no registers tied up), the warps feed DMMA
-// from the slab.  Columns sit 128 bytes apart with the 16-byte chunks XOR-swizzled on the column
-// parity, so the four-lane k groups of two neighbouring columns hit different banks.  The ring
-// lives in the packed-Gram region, which is dead while the block is being rebuilt.  Summation
-// order per element is that of gram_P.  Returns false when the ring does not fit.
-template <int T>
-__device__ __noinline__ bool gram_P_slab_fn(const double* __restrict__ Xs, int ldx, const int* ia, int m,
-                                               const double* wv, double* Hsm, int hs_cap, double* H) {
-  {
-    constexpr int ldh = kNX;
-    const int tid = threadIdx.x;
-    constexpr int R = 16;
-    const int slab_d = m * R;
-    int ns = slab_d > 0 ? hs_cap / slab_d : 0;
-    if (ns < 2) return false;
-    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5, g8 = lane >> 2, t4 = lane & 3;
-    const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2, nslab = ldx / R;
-    const int nchunk = m * (R / 2);
-    auto issue = [&](int sl, int stage) {
-      double* dst = Hsm + stage * slab_d;
-      const double* src = Xs + (size_t)sl * R;
-      for (int c = tid; c < nchunk; c += T) {
-        const int cl = c >> 3, ch = c & 7;
-        cpa16(dst + cl * R + ((ch ^ ((cl & 1) << 2)) << 1), src + (size_t)ia[cl] * ldx + ch * 2);
-      }
-    };
-    auto run = [&](auto nsc) {
-      constexpr int NS = decltype(nsc)::value;
-      for (int t0 = 0; t0 < ntile; t0 += 2 * nw) {  // a pass: two tiles per warp
-        int cI[2][2], cJ[2][2], TI[2], TJ[2];
-        bool live[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int tix = t0 + warp + q * nw;
-          live[q] = tix < ntile;
-          int J = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
-          while ((J + 1) * (J + 2) / 2 <= tix) ++J;
-          while (J * (J + 1) / 2 > tix) --J;
-          const int I = tix - J * (J + 1) / 2;
-          TI[q] = I; TJ[q] = J;
-          auto cl = [&](int idx) { return idx < m ? idx : m - 1; };
-          cI[q][0] = cl(I * 16 + g8); cI[q][1] = cl(I * 16 + 8 + g8);
-          cJ[q][0] = cl(J * 16 + g8); cJ[q][1] = cl(J * 16 + 8 + g8);
-        }
-        double acc[2][8];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[q][e] = 0.0;
-        __syncthreads();  // the ring is free (previous pass / previous user of the region)
-#pragma unroll
-        for (int sl = 0; sl < NS - 1; ++sl) {
-          if (sl < nslab) issue(sl, sl);
-          cpa_commit();
-        }
-        for (int sl = 0; sl < nslab; ++sl) {
-          cpa_wait<NS - 2>();
-          __syncthreads();  // slab sl has landed for everyone; slab sl-1 is fully consumed
-          if (sl + NS - 1 < nslab) issue(sl + NS - 1, (sl + NS - 1) % NS);
-          cpa_commit();
-          const double* st = Hsm + (sl % NS) * slab_d;
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const double2 w = *reinterpret_cast<const double2*>(wv + sl * R + kk * 8 + 2 * t4);
-            const int ch = kk * 4 + t4;
-            auto ld = [&](int cl) {
-              return *reinterpret_cast<const double2*>(st + cl * R + ((ch ^ ((cl & 1) << 2)) << 1));
-            };
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              if (!live[q]) continue;
-              const double2 a0 = ld(cI[q][0]), a1 = ld(cI[q][1]);
-              double2 b0 = ld(cJ[q][0]), b1 = ld(cJ[q][1]);
-              b0.x *= w.x; b0.y *= w.y; b1.x *= w.x; b1.y *= w.y;
-              dmma(acc[q][0], acc[q][1], a0.x, b0.x);
-              dmma(acc[q][2], acc[q][3], a0.x, b1.x);
-              dmma(acc[q][4], acc[q][5], a1.x, b0.x);
-              dmma(acc[q][6], acc[q][7], a1.x, b1.x);
-              dmma(acc[q][0], acc[q][1], a0.y, b0.y);
-              dmma(acc[q][2], acc[q][3], a0.y, b1.y);
-              dmma(acc[q][4], acc[q][5], a1.y, b0.y);
-              dmma(acc[q][6], acc[q][7], a1.y, b1.y);
-            }
-          }
-        }
-        cpa_wait<0>();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (!live[q]) continue;
-#pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int r = TI[q] * 16 + a * 8 + g8, cc = TJ[q] * 16 + b * 8 + 2 * t4 + e;
-                if (r < m && cc < m && (TI[q] != TJ[q] || r <= cc)) {
-                  const double v = acc[q][a * 4 + b * 2 + e];
-                  H[r + (size_t)cc * ldh] = v;
-                  H[cc + (size_t)r * ldh] = v;
-                }
-              }
-        }
-      }
-    };
-    if (ns >= 4) run(std::integral_constant<int, 4>());
-    else if (ns == 3) run(std::integral_constant<int, 3>());
-    else run(std::integral_constant<int, 2>());
-    __syncthreads();
-    return true;
-  }
 }
 
 // One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane).  The
@@ -1363,9 +1347,12 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     if (timing) { const long long t = clock64(); tph[k] += t - tmark; tmark = t; }
   };
   int ninact = 0;
-  int* INc = A.ws.INACT + (size_t)list[blockIdx.x] * A.p_pad;
+  // The list is in completion order of the previous round (quick problems first); taking it from
+  // the back starts the long-running problems first, so the round does not end on stragglers.
+  const int lpos = (A.prm.dbg & 2048) ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
+  int* INc = A.ws.INACT + (size_t)list[lpos] * A.p_pad;
   const long long t_start = clock64();
-  const int pid = list[blockIdx.x];
+  const int pid = list[lpos];
   LassoProb* PR = A.ws.prob + pid;
   const int g = PR->gene, fit = PR->fit, slot = PR->slot;
   int state = PR->state, lidx = PR->lidx, lmu = PR->lmu, nin = PR->nin, nS = PR->nS;
@@ -1568,28 +1555,37 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // (one warp per column, independent accumulators per lane, no block barrier inside)
   auto gram_vectors = [&](int l0, int l1, bool with_p) {
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    if (mlp) {
+      for (int lb = l0 + 4 * warp; lb < l1; lb += 4 * nw) {
+        const double* zc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)ia[lb + c < l1 ? lb + c : lb] * ldx;
+        double ps4[4], rs4[4];
+        wdot_wr4(zc[0], zc[1], zc[2], zc[3], wv, wrv, ldx, ps4, rs4);
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (lb + c < l1) {
+              if (with_p) swa[lb + c] = ps4[c];
+              gq[lb + c] = rs4[c];
+            }
+        }
+      }
+    } else
     for (int l = l0 + warp; l < l1; l += nw) {
       const double* c = Xs + (size_t)ia[l] * ldx;
-      double ps, rs;
-      if (mlp) {
-        const double2 pr = wdot_wr(c, wv, wrv, ldx);
-        ps = pr.x;
-        rs = pr.y;
-      } else {
-        double pa = 0.0, pb = 0.0, ra = 0.0, rb = 0.0;
+      double pa = 0.0, pb = 0.0, ra = 0.0, rb = 0.0;
 #pragma unroll 4
-        for (int i = 2 * lane; i < ldx; i += 64) {
-          const double2 x = ldg2(c + i);
-          const double2 w = *reinterpret_cast<const double2*>(wv + i);
-          const double2 r = *reinterpret_cast<const double2*>(wrv + i);
-          pa += w.x * x.x;
-          pb += w.y * x.y;
-          ra += r.x * x.x;
-          rb += r.y * x.y;
-        }
-        ps = warp_sum(pa + pb);
-        rs = warp_sum(ra + rb);
+      for (int i = 2 * lane; i < ldx; i += 64) {
+        const double2 x = ldg2(c + i);
+        const double2 w = *reinterpret_cast<const double2*>(wv + i);
+        const double2 r = *reinterpret_cast<const double2*>(wrv + i);
+        pa += w.x * x.x;
+        pb += w.y * x.y;
+        ra += r.x * x.x;
+        rb += r.y * x.y;
       }
+      const double ps = warp_sum(pa + pb), rs = warp_sum(ra + rb);
       if (lane == 0) {
         if (with_p) swa[l] = ps;
         gq[l] = rs;
@@ -1641,12 +1637,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     }
     gram_fma += (unsigned long long)ntile * 256ull * (unsigned)ldx;
     __syncthreads();
-  };
-  auto gram_P_slab = [&](int m) -> bool {
-    if (!gram_P_slab_fn<T>(Xs, ldx, ia, m, wv, Hsm, A.hs_cap, H)) return false;
-    const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2;
-    gram_fma += (unsigned long long)ntile * 256ull * (unsigned)ldx;
-    return true;
   };
   // per-fit standardisation of the raw moments: H and v (-> va) ...
   auto gram_finish_H = [&](int m) {
@@ -1845,12 +1835,30 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     // new Gram column against the m current members: one warp per member, no block barrier
     {
       const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-      for (int l = warp; l < m; l += nw) {
-        const double* c = Xs + (size_t)ia[l] * ldx;
-        double acc;
-        if (mlp) {
-          acc = wdot_wxz(c, col, wv, ldx);
-        } else {
+      auto put = [&](int l, double acc) {  // lane 0: standardise, store the new row / column
+        const double pl = swa[l] / xia[l] + xma[l] * v0m;  // raw sum w Xs_l back from h0_l
+        const double h = xia[l] * xi * (acc - xma[l] * d2[0] - xm * pl + xma[l] * xm * v0);
+        H[l + (size_t)m * ldh] = h;
+        H[m + (size_t)l * ldh] = h;
+        if (grow) hrow[l] = h;
+        gq[l] -= d * h;
+      };
+      if (mlp) {
+        for (int lb = 4 * warp; lb < m; lb += 4 * nw) {
+          const double* zc[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)ia[lb + c < m ? lb + c : lb] * ldx;
+          double acc4[4];
+          wdot_wxz4(zc[0], zc[1], zc[2], zc[3], col, wv, ldx, acc4);
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (lb + c < m) put(lb + c, acc4[c]);
+          }
+        }
+      } else {
+        for (int l = warp; l < m; l += nw) {
+          const double* c = Xs + (size_t)ia[l] * ldx;
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
           for (int i = 2 * lane; i < ldx; i += 64) {
@@ -1860,15 +1868,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             s0 += w.x * x.x * z.x;
             s1 += w.y * x.y * z.y;
           }
-          acc = warp_sum(s0 + s1);
-        }
-        if (lane == 0) {
-          const double pl = swa[l] / xia[l] + xma[l] * v0m;  // raw sum w Xs_l back from h0_l
-          const double h = xia[l] * xi * (acc - xma[l] * d2[0] - xm * pl + xma[l] * xm * v0);
-          H[l + (size_t)m * ldh] = h;
-          H[m + (size_t)l * ldh] = h;
-          if (grow) hrow[l] = h;
-          gq[l] -= d * h;
+          const double acc = warp_sum(s0 + s1);
+          if (lane == 0) put(l, acc);
         }
       }
       ncols += m;
@@ -1922,13 +1923,32 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       __syncthreads();
       int j0 = 0;
       while (j0 < cn) {
-        for (int j = j0 + warp; j < cn; j += nw) {
-          if (mpos[j] < 0) {
-            const double* c = Xs + (size_t)mk[j] * ldx;
-            double acc;
-            if (mlp) {
-              acc = wdot_a(c, wrv, ldx);
-            } else {
+        if (mlp) {
+          for (int jb = j0 + 4 * warp; jb < cn; jb += 4 * nw) {
+            const double* zc[4];
+            bool need[4], any = false;
+            int first = -1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              need[c] = jb + c < cn && mpos[jb + c] < 0;
+              any |= need[c];
+              if (need[c] && first < 0) first = jb + c;
+            }
+            if (!any) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)mk[need[c] ? jb + c : first] * ldx;
+            double acc4[4];
+            wdot_a4(zc[0], zc[1], zc[2], zc[3], wrv, ldx, acc4);
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (need[c]) mg[jb + c] = mxi[jb + c] * (acc4[c] - mxm[jb + c] * q0);
+            }
+          }
+        } else {
+          for (int j = j0 + warp; j < cn; j += nw) {
+            if (mpos[j] < 0) {
+              const double* c = Xs + (size_t)mk[j] * ldx;
               double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
               for (int i = 2 * lane; i < ldx; i += 64) {
@@ -1937,9 +1957,9 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
                 s0 += r.x * x.x;
                 s1 += r.y * x.y;
               }
-              acc = warp_sum(s0 + s1);
+              const double acc = warp_sum(s0 + s1);
+              if (lane == 0) mg[j] = mxi[j] * (acc - mxm[j] * q0);
             }
-            if (lane == 0) mg[j] = mxi[j] * (acc - mxm[j] * q0);
           }
         }
         __syncthreads();
@@ -2021,7 +2041,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         gram_vectors(0, m, rebuild);
         lap(1);
         if (rebuild) {
-          if ((dbg & 512) || !gram_P_slab(m)) gram_P(m);
+          gram_P(m);
           gram_finish_H(m);
           v0m = v0;
           H_valid = true;
@@ -2065,7 +2085,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             // with the current weights (then it is one, and coordinate descent converges).
             materialise(m);
             gram_vectors(0, m, true);
-            if ((dbg & 512) || !gram_P_slab(m)) gram_P(m);
+            gram_P(m);
             gram_finish_H(m);
             v0m = v0;
             gram_finish_vec(m, true);
@@ -2406,9 +2426,18 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-int lasso_max_block(int NF) {
-  int tot = 6144;  // problems in flight per block: enough waves to even out uneven problems
+int lasso_max_block(int NF, const DesignState& D) {
+  // problems in flight per block: enough waves that a round does not end on a part-filled one
+  // (12,288 = 41 waves of 296 resident CTAs), bounded by a third of the free device memory
+  int tot = 12288;
   if (const char* e = getenv("SAVER_LASSO_PROBLEMS")) tot = atoi(e);
+  const double per_problem = (double)D.ldx * 8 * 3 + (double)D.p_pad * (8 * 3 + 4 * 3) + (double)kNX * 28;
+  const double per_gene = NF * per_problem + (double)kNLam * (kNX * 8 + kMaxFolds * 8 + 32);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    const double cap = ((double)free_b / 3.0 - (double)kHSlots * kNX * kNX * 8) / per_gene;
+    if (cap * NF < tot) tot = (int)(cap > 1.0 ? cap * NF : NF);
+  }
   int b = tot / NF;
   return b < 1 ? 1 : b;
 }
@@ -2532,7 +2561,6 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     int mh = 0;
     while (mh < 256 && (size_t)(mh + 1) * (mh + 2) / 2 * 8 <= hs) ++mh;
     A.mh = mh;
-    A.hs_cap = mh * (mh + 1) / 2;
     smem_gram += (size_t)mh * (mh + 1) / 2 * 8;
     smem_gram = (smem_gram + 15) / 16 * 16;
   }

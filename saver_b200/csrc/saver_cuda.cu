@@ -296,7 +296,7 @@ int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int
   prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg;
   prm.alf_wide = lambda_ratio(0.01, nlambda);
   prm.alf_tall = lambda_ratio(1e-4, nlambda);
-  const int chunk = lasso_max_block(prm.NF);
+  const int chunk = lasso_max_block(prm.NF, D);
   for (int b0 = 0; b0 < B; b0 += chunk) {
     prm.B = B - b0 < chunk ? B - b0 : chunk;
     CU(lasso_run(D, h->lasso, prm, dY.d + n * b0, dFold.d + n * b0, dSelf.d ? dSelf.d + b0 : nullptr,
@@ -366,7 +366,7 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
   prm.NF = 1; prm.nfolds = 0; prm.auto_lambda = 0; prm.dfmax = dfmax; prm.nlam = 0;
   prm.thr = thresh; prm.maxit = 100000;
   prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.alf_wide = prm.alf_tall = 1.0;
-  const int chunk = lasso_max_block(prm.NF);
+  const int chunk = lasso_max_block(prm.NF, D);
   DevBuf<int> fold;
   DevBuf<double> fit4;
   CU(fold.alloc(n * (size_t)(B < chunk ? B : chunk), s));
