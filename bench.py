@@ -240,13 +240,21 @@ def run_cuda(args):
     gemm_s = dc[1] / 1e3
     gemm_flops = dc[5] * 2.0 * n * p
     kname = "lasso_round_gram_kernel" if os.environ.get("SAVER_LASSO_GRAM", "1") != "0" else "lasso_round_kernel"
+    # DRAM bytes of one launch of that kernel from the committed ncu --set full capture
+    traffic, tnote = None, ""
+    tp = os.path.join(ROOT, "profiles", "r1b_round_kernel_traffic.json")
+    if kname == "lasso_round_gram_kernel" and os.path.exists(tp):
+        td = json.load(open(tp))
+        traffic = td["dram_bytes_per_launch"]
+        tnote = (" traffic = dram read + write of the captured launch (%s); the same launch moved %.0f GB "
+                 "from L2 to the SMs" % (td["capture"], td["l2_to_sm_bytes_per_launch"] / 1e9))
     roof = {"kernel": kname, "bound": "hbm",
             "achieved": col_bytes / round_s / 1e9 if round_s > 0 else None, "peak": hbm,
             "unit": "GB/s", "frac": (col_bytes / round_s / 1e9 / hbm) if round_s > 0 else None,
-            "traffic": None, "peak_source": which,
+            "traffic": traffic, "peak_source": which,
             "note": "algorithmic bytes = design columns streamed x n x 8 B (counted in-kernel) over the "
-                    "CUDA-event time of the round kernels; the columns are served by L2 (97% hits), the "
-                    "kernel is latency bound (profiles/README.md)",
+                    "CUDA-event time of the round kernels; the columns are served by L2 (80% hits), the "
+                    "kernel is latency bound (profiles/README.md)." + tnote,
             "gram_dmma_tflops_inside_kernel": gram_flops / round_s / 1e12 if round_s > 0 else None,
             "share_of_step": {kname: round_s / tmax, "gemm_tn_f64_kernel": gemm_s / tmax,
                               "lasso_setup": dc[2] / 1e3 / tmax, "calc_post_kernel": dc[3] / 1e3 / tmax},

@@ -84,6 +84,22 @@ cor.genes <- function(x, cor.mat = NULL)
 cor.cells <- function(x, cor.mat = NULL)
   .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(x$se), TRUE, cor.mat)
 
+# sparse input (dgCMatrix): upload the slots once; row blocks and x.est are densified on the device.
+# In saver() (R/saver.R:156-157) and calc.estimate (R/calc_estimate.R:69) replace
+#   x.est <- t(as.matrix(log(sweep(x[good.genes, ] + 1, 2, sf, "/"))))   by   saver.cuda.log.rows(good.genes, sf)
+#   as.matrix(x[block, ])                                                by   t(saver.cuda.rows(block))
+saver.cuda.set.counts <- function(x) {
+  stopifnot(methods::is(x, "dgCMatrix"))
+  .Call(C_saver_cuda_set_counts_csc, saver.cuda.handle(), x@p, x@i, as.numeric(x@x), dim(x))
+  sums <- .Call(C_saver_cuda_csc_sums, saver.cuda.handle(), dim(x))
+  list(col.sums = sums[[1]], row.sums = sums[[2]], ncells = ncol(x))
+}
+saver.cuda.rows <- function(genes, ncells)
+  .Call(C_saver_cuda_csc_gather, saver.cuda.handle(), as.integer(genes - 1L), NULL, ncells)
+saver.cuda.log.rows <- function(genes, sf)
+  .Call(C_saver_cuda_csc_gather, saver.cuda.handle(), as.integer(genes - 1L), as.numeric(sf),
+        length(sf))
+
 # saver(), saver.fit(), saver.fit.mean/.null, get.mu, combine.saver and R/utils.R stay as they are
 # in the reference (they only call the functions above); saver() forces ncores to one process:
 #   if (ncores > 1) message("libsaver_cuda: device parallelism replaces ", ncores, " PSOCK workers")

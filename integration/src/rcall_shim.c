@@ -147,6 +147,41 @@ SEXP C_saver_cuda_cor_adjust(SEXP hp, SEXP est_t, SEXP se_t, SEXP by_cells, SEXP
     return out;
 }
 
+/* dgCMatrix slots (x@p, x@i, x@x) -> resident sparse counts; replaces the Matrix-package work of
+ * R/saver.R:156-157 and as.matrix(x[block, ]) of R/calc_estimate.R:69 */
+SEXP C_saver_cuda_set_counts_csc(SEXP hp, SEXP p, SEXP i, SEXP xv, SEXP dim)
+{
+    saver_cuda_handle h = get_handle(hp);
+    check(h, saver_cuda_set_counts_csc(h, INTEGER(p), INTEGER(i), REAL(xv), INTEGER(dim)[0],
+                                       INTEGER(dim)[1]));
+    return R_NilValue;
+}
+
+SEXP C_saver_cuda_csc_sums(SEXP hp, SEXP dim)
+{
+    saver_cuda_handle h = get_handle(hp);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP cs = PROTECT(Rf_allocVector(REALSXP, INTEGER(dim)[1]));
+    SEXP rs = PROTECT(Rf_allocVector(REALSXP, INTEGER(dim)[0]));
+    check(h, saver_cuda_csc_sums(h, REAL(cs), REAL(rs)));
+    SET_VECTOR_ELT(out, 0, cs);
+    SET_VECTOR_ELT(out, 1, rs);
+    UNPROTECT(3);
+    return out;
+}
+
+/* t(as.matrix(x[genes, ])) (n x B), or t(log((x[genes, ] + 1) / sf)) when sf is not NULL */
+SEXP C_saver_cuda_csc_gather(SEXP hp, SEXP genes0, SEXP sf, SEXP ncells)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int B = Rf_length(genes0), n = Rf_asInteger(ncells);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, B));
+    check(h, saver_cuda_csc_gather(h, INTEGER(genes0), B, Rf_isNull(sf) ? NULL : REAL(sf),
+                                   !Rf_isNull(sf), REAL(out), 0));
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_saver_cuda_create", (DL_FUNC)&C_saver_cuda_create, 1},
     {"C_saver_cuda_set_design", (DL_FUNC)&C_saver_cuda_set_design, 2},
@@ -157,6 +192,9 @@ static const R_CallMethodDef call_methods[] = {
     {"C_saver_cuda_maxcor", (DL_FUNC)&C_saver_cuda_maxcor, 3},
     {"C_saver_cuda_sample", (DL_FUNC)&C_saver_cuda_sample, 6},
     {"C_saver_cuda_cor_adjust", (DL_FUNC)&C_saver_cuda_cor_adjust, 5},
+    {"C_saver_cuda_set_counts_csc", (DL_FUNC)&C_saver_cuda_set_counts_csc, 5},
+    {"C_saver_cuda_csc_sums", (DL_FUNC)&C_saver_cuda_csc_sums, 2},
+    {"C_saver_cuda_csc_gather", (DL_FUNC)&C_saver_cuda_csc_gather, 4},
     {NULL, NULL, 0}};
 
 void R_init_SAVERcuda(DllInfo* dll)

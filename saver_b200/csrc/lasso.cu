@@ -1392,8 +1392,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     wrv = WRg;
   } else {
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
-      *reinterpret_cast<double2*>(wv + i) = *reinterpret_cast<const double2*>(Wg + i);
-      *reinterpret_cast<double2*>(wrv + i) = *reinterpret_cast<const double2*>(WRg + i);
+      *reinterpret_cast<double2*>(wv + i) = __ldcs(reinterpret_cast<const double2*>(Wg + i));
+      *reinterpret_cast<double2*>(wrv + i) = __ldcs(reinterpret_cast<const double2*>(WRg + i));
     }
   }
   for (int l = tid; l < nin; l += T) {
@@ -1409,9 +1409,9 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   auto mark_pass = [&](double thresh) -> int {
     int cnt = 0;
     for (int j = tid; j < p; j += T) {
-      const double xi = XIc[j];
+      const double xi = __ldcs(XIc + j);
       if (xi != 0.0 && MMc[j] == 0) {
-        const double ga = fabs((Gc[j] - XMc[j] * sumr) * xi);
+        const double ga = fabs((__ldcs(Gc + j) - __ldcs(XMc + j) * sumr) * xi);
         if (ga > thresh) {
           MMc[j] = -1;
           ++cnt;
@@ -1428,10 +1428,10 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   auto mark_reset = [&](double thresh) -> int {
     int cnt = 0;
     for (int j = tid; j < p; j += T) {
-      const double xi = XIc[j];
+      const double xi = __ldcs(XIc + j);
       const int mm = MMc[j];
       if (xi != 0.0 && mm <= 0) {
-        const double ga = fabs((Gc[j] - XMc[j] * sumr) * xi);
+        const double ga = fabs((__ldcs(Gc + j) - __ldcs(XMc + j) * sumr) * xi);
         const int nm = ga > thresh ? -1 : 0;
         if (nm != mm) {
           MMc[j] = nm;
@@ -1448,8 +1448,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     if (master_auto) {
       double m = 0.0;
       for (int j = tid; j < p; j += T) {
-        const double xi = XIc[j];
-        if (xi != 0.0) m = fmax(m, fabs((Gc[j] - XMc[j] * sumr) * xi));
+        const double xi = __ldcs(XIc + j);
+        if (xi != 0.0) m = fmax(m, fabs((__ldcs(Gc + j) - __ldcs(XMc + j) * sumr) * xi));
       }
       m = bmax(m, red, phase);
       if (tid == 0) {  // the null model is solution 0 (lambda = "big")
@@ -2179,8 +2179,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   __syncthreads();
   if (STAGED) {
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
-      *reinterpret_cast<double2*>(Wg + i) = *reinterpret_cast<const double2*>(wv + i);
-      *reinterpret_cast<double2*>(WRg + i) = *reinterpret_cast<const double2*>(wrv + i);
+      __stcs(reinterpret_cast<double2*>(Wg + i), *reinterpret_cast<const double2*>(wv + i));
+      __stcs(reinterpret_cast<double2*>(WRg + i), *reinterpret_cast<const double2*>(wrv + i));
     }
   }
   for (int l = tid; l < nin && l < kNX; l += T) {

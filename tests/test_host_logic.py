@@ -140,3 +140,18 @@ def test_saver_null_and_pred_gene_arguments():
     sub = saver_b200.saver(x, do_fast=False, pred_genes=np.array([3, 4]), pred_genes_only=True,
                            backend=OracleBackend(), fold_seed=0)
     assert sub.estimate.shape[0] == 2
+
+
+def test_saver_sparse_input_equals_dense_on_the_host_path():
+    # scipy.sparse input (R: dgCMatrix): clean.data, size factors, gene filters and the row blocks
+    # handed to calc.estimate are the same as for the dense matrix (R/utils.R:2-31, R/saver.R:156)
+    import scipy.sparse as sp
+    import saver_b200
+    x = _small()[:36]
+    x[:, 7] = 0                                       # an all-zero cell is dropped
+    x[4, :5] = 0.0004                                 # below clean.data's threshold
+    a = saver_b200.saver(x, do_fast=False, backend=OracleBackend(), fold_seed=2)
+    b = saver_b200.saver(sp.csr_matrix(x), do_fast=False, backend=OracleBackend(), fold_seed=2)
+    assert a.estimate.shape == (36, x.shape[1] - 1)
+    assert np.array_equal(a.estimate, b.estimate) and np.array_equal(a.se, b.se)
+    assert np.array_equal(a.info["size.factor"], b.info["size.factor"])
