@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) lasso_setup_kernel(RoundArgs A) {
   if (tid == 0) {
     LassoProb pr;
     pr.gene = g; pr.fit = fit; pr.state = ST_INIT; pr.lidx = 0; pr.lmu = 0; pr.nin = 0; pr.nS = 0;
-    pr.jerr = 0; pr.nlp = 0; pr.ngrad = 0; pr.mtrain = mtrain; pr.slot = pid;
+    pr.jerr = 0; pr.nlp = 0; pr.ngrad = 0; pr.mtrain = mtrain; pr.slot = pid; pr.resumed = 0;
     pr.al = 0; pr.al0 = 0; pr.qv = qv; pr.yb = yb;
     pr.az = 0; pr.dv0 = 0; pr.dvr = 0; pr.shr = 0; pr.v0 = yb; pr.sumr = 0;
     pr.cur_dev = 0; pr.cur_cv = 0; pr.ncv = v3[1];
@@ -1357,6 +1357,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   const int g = PR->gene, fit = PR->fit, slot = PR->slot;
   int state = PR->state, lidx = PR->lidx, lmu = PR->lmu, nin = PR->nin, nS = PR->nS;
   int jerr = PR->jerr, nlp = PR->nlp;
+  bool force_irls = PR->resumed != 0;  // resumed mid-solve: the next outer check cannot be the last
+  bool yielded = false, yielded_mid = false;  // gave up the time slice (mid: inside an IRLS step)
   double al = PR->al, al0 = PR->al0, az = PR->az, v0 = PR->v0, sumr = PR->sumr;
   double cur_dev = PR->cur_dev, cur_cv = PR->cur_cv;
   const double qv = PR->qv, dv0 = PR->dv0, dvr = PR->dvr, shr = PR->shr, ncv = PR->ncv;
@@ -1985,6 +1987,15 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     }
   };
 
+  // Time slice.  A round ends when its slowest problem does, and a few (gene, lambda) pairs need
+  // thousands of sweeps (glmnet's maxit is 1e5): such a problem gives up the SM after its slice,
+  // leaves a consistent n-space state (coefficients, intercept, w, wr materialised) and continues
+  // in the next round from state ST_SOLVE, while the other problems move on to their next lambda.
+  const long long slice = A.prm.slice_cycles;
+  auto slice_over = [&]() -> bool {
+    return slice > 0 && __syncthreads_or(tid == 0 && clock64() - t_start > slice);
+  };
+
   if (state == ST_SOLVE) {
     // inactive members of the strong set, in index order
     {
@@ -2079,6 +2090,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
           if (dlx < shr) break;
           if (!(dlx == dlx)) { nanfail = true; break; }
           if (nlp > maxit) { maxed = true; break; }
+          if ((inner & 7) == 7 && slice_over()) { yielded = true; break; }
           if (++inner >= 64 && !H_fresh && m > 0) {
             // A model that mixes weights of several IRLS steps (kept block + rows of variables that
             // entered later) is not guaranteed to be a Gram matrix; if the sweeps stall, rebuild it
@@ -2095,7 +2107,14 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             inner = 0;
           }
         }
-        if (maxed || nanfail) break;
+        if (maxed || nanfail || yielded) break;
+        if (slice_over()) { yielded = true; break; }
+      }
+      if (yielded) {  // n-space state of the current iterate; the solve resumes next round
+        materialise(m);
+        sumr = q0;
+        yielded_mid = true;
+        break;
       }
       if (overflow) { jerr = -10000 - (lidx + 1); state = ST_DONE; break; }
       if (maxed) { jerr = -(lidx + 1); state = ST_DONE; break; }
@@ -2168,10 +2187,13 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         bad |= va[l] * d * d >= shr;
       }
       lap(6);
+      if (force_irls) bad = 1;
+      force_irls = false;
       if (!__syncthreads_or(bad)) {
         state = ST_WAIT_KKT;
         break;
       }
+      if (slice_over()) { yielded = true; break; }  // w, wr are the fresh linearisation: nothing to save
     }
   }
 
@@ -2214,7 +2236,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     atomicAdd(A.ws.colcount + 3, (unsigned long long)(state == ST_WAIT_KKT || state == ST_DONE));
     if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
     PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
-    PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
+    PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1; PR->resumed = yielded_mid ? 1 : 0;
     PR->al = al; PR->al0 = al0; PR->az = az; PR->v0 = v0; PR->sumr = sumr;
     PR->cur_dev = cur_dev; PR->cur_cv = cur_cv;
   }
@@ -2501,6 +2523,8 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   A.prm = prm;
   if (const char* e = getenv("SAVER_LASSO_DBG")) A.prm.dbg = atoi(e);
   if (const char* e = getenv("SAVER_STRONG_SLACK")) A.prm.strong_slack = atof(e);
+  A.prm.slice_cycles = 15000LL * ldx;  // ~15 ms at n = 2,000: several times a typical (problem, lambda)
+  if (const char* e = getenv("SAVER_SLICE_CYCLES")) A.prm.slice_cycles = atoll(e);
   A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
 
   if ((e = cudaMemsetAsync(ws.counters, 0, 64, s)) != cudaSuccess) return e;

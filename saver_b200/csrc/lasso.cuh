@@ -23,6 +23,7 @@ struct LassoProb {
   int ngrad;    // full-gradient (X^T r over all p) rounds so far
   int mtrain;   // training rows
   int slot;     // column of R / G this problem used in the last round
+  int resumed;  // the last launch gave up its time slice mid-solve: force one more IRLS step
   double al, al0;   // current / previous lambda
   double az;        // intercept
   double qv;        // observation weight 1 / mtrain
@@ -47,6 +48,7 @@ struct LassoParams {
   double alf_tall;  // lambda ratio for flmin = 1e-4
   int gram = 1;     // 1: Gram-space round kernel (default), 0: n-space kernel that mirrors fishnet1's iterate sequence
   double strong_slack = 1.0;  // screening margin below lambda in units of the lambda step (1 = strong rule)
+  long long slice_cycles = 0;  // time slice of a round-kernel CTA in SM cycles (0: none), set by lasso_run
   int dbg = 0;      // bisection switches for bring-up (SAVER_LASSO_DBG), 0 in production
 };
 

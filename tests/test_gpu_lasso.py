@@ -138,3 +138,25 @@ def test_predict_edge_cases(handle):
             assert _rel(got["mu"][g], ref["mu"]).max() < 1e-2
         if ref["rc"] != 0:
             assert np.allclose(got["mu"][g], ref["mu"])
+
+
+def test_time_slices_resume_to_the_same_solution(handle, monkeypatch):
+    """A round-kernel CTA gives up the SM after its time slice and resumes next round from a
+    materialised n-space state.  With slices so short that every problem is cut many times the
+    solver must arrive at the same path (same lambda.min, mu within the convergence error)."""
+    G, n = 260, 400
+    x = synth.nb_counts(G, n, seed=11).astype(np.float64)
+    sf = x.sum(0) / x.sum(0).mean()
+    good = np.where(x.mean(1) >= 0.1)[0]
+    ops.set_design(np.log((x[good] + 1.0) / sf), handle=handle)
+    sel = good[:48]
+    self_col = np.arange(48, dtype=np.int32)
+    fold = _folds(48, n, 5, 3)
+    ref = ops.predict_cv(x[sel] / sf, fold, self_col=self_col, want_stats=True, handle=handle)
+    monkeypatch.setenv("SAVER_SLICE_CYCLES", "400000")
+    cut = ops.predict_cv(x[sel] / sf, fold, self_col=self_col, want_stats=True, handle=handle)
+    assert (cut["stats"][:, 3] > ref["stats"][:, 3]).all()        # more rounds: the slices did cut
+    assert (cut["status"] == ref["status"]).all()
+    assert np.mean(cut["idx"] == ref["idx"]) >= 0.9
+    same = cut["idx"] == ref["idx"]
+    assert np.median(_rel(cut["mu"][same], ref["mu"][same])) < 1e-4
