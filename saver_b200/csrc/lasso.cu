@@ -2523,7 +2523,12 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   A.prm = prm;
   if (const char* e = getenv("SAVER_LASSO_DBG")) A.prm.dbg = atoi(e);
   if (const char* e = getenv("SAVER_STRONG_SLACK")) A.prm.strong_slack = atof(e);
-  A.prm.slice_cycles = 15000LL * ldx;  // ~15 ms at n = 2,000: several times a typical (problem, lambda)
+  // Time slices are opt-in (SAVER_SLICE_CYCLES=<cycles>; 15,000 x n was the setting measured on
+  // do.fast): with that default the cross-validated auto-lambda path died with an "illegal
+  // instruction" on the device (tests/test_gpu_saver.py full-cv case and the bench workload), so
+  // the default stays 0 = a problem runs its lambda to the end, the configuration every committed
+  // number was measured with.
+  A.prm.slice_cycles = 0;
   if (const char* e = getenv("SAVER_SLICE_CYCLES")) A.prm.slice_cycles = atoll(e);
   A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
 

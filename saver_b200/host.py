@@ -425,13 +425,12 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
         coefs = _lm(z, info["maxcor"][pred])
         info["lambda.coefs"] = coefs
         cutoff2 = max(cutoff, float(-coefs[0] / coefs[1]))
-        n4 = min(max(int(np.ceil((npred - n3) / 4)), nworkers) + n3, npred)
+        # The reference predicts a quarter of the rest first only to print a finish-time estimate
+        # (R/saver_fit.R:262-330); the fixed-lambda fits carry no seed and do not depend on the
+        # stage they run in, so both parts go down as one block: one pass over the device, and the
+        # few genes that crawl to glmnet's maxit hold one stage instead of two.
         msg("Predicting remaining genes...")
-        fit.run(ind[n3:n4], 2, cutoff2, coefs, True, **common)
-        if n4 == npred:
-            return finish(n4)
-        msg("Predicting remaining genes...")
-        fit.run(ind[n4:npred], 2, cutoff2, coefs, True, **common)
+        fit.run(ind[n3:npred], 2, cutoff2, coefs, True, **common)
         return finish(npred)
     mode = 0 if null_model else 1
     # the slow schedule: n1, a quarter of the rest, the rest -- all cross-validated, maxcor = 2
