@@ -66,13 +66,25 @@ calc.maxcor <- function(x1, x2) {
   .Call(C_saver_cuda_maxcor, h, x2, as.integer(self.col))
 }
 
+# Legacy objects list(estimate, alpha, beta, info) (R/utils.R:137-232: sample.saver.old,
+# cor.genes.old, cor.cells.old) run on the same kernels through equivalent (mean, sd) panels:
+# gamma draws and the correlation adjustment use mean = alpha/beta, sd = sqrt(alpha)/beta
+# (shape = mean^2/sd^2 = alpha, rate = mean/sd^2 = beta, sd^2 = alpha/beta^2); NB draws use
+# mean = estimate, sd = estimate/sqrt(alpha) (size = alpha).
+.saver.moments <- function(x, efficiency.known = FALSE) {
+  if (is.null(x$alpha)) return(list(est = x$estimate, se = x$se))
+  if (efficiency.known) return(list(est = x$estimate, se = x$estimate / sqrt(x$alpha)))
+  list(est = x$alpha / x$beta, se = sqrt(x$alpha) / x$beta)
+}
+
 # replaces R/sample_saver.R:32-79 and R/cor_adjust.R:26-66
 sample.saver <- function(x, rep = 1, efficiency.known = FALSE, seed = NULL) {
   rep <- as.integer(rep)
   if (rep <= 0) stop("rep must be a positive integer.")
   if (is.null(seed)) seed <- sample.int(.Machine$integer.max, 1)
+  m <- .saver.moments(x, efficiency.known)
   draw <- function(j) {
-    s <- t(.Call(C_saver_cuda_sample, saver.cuda.handle(), t(x$estimate), t(x$se),
+    s <- t(.Call(C_saver_cuda_sample, saver.cuda.handle(), t(m$est), t(m$se),
                  as.logical(efficiency.known), as.numeric(seed), as.integer(j - 1L)))
     dimnames(s) <- dimnames(x$estimate)
     s
@@ -80,9 +92,9 @@ sample.saver <- function(x, rep = 1, efficiency.known = FALSE, seed = NULL) {
   if (rep == 1) draw(1L) else lapply(seq_len(rep), draw)
 }
 cor.genes <- function(x, cor.mat = NULL)
-  .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(x$se), FALSE, cor.mat)
+  .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(.saver.moments(x)$se), FALSE, cor.mat)
 cor.cells <- function(x, cor.mat = NULL)
-  .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(x$se), TRUE, cor.mat)
+  .Call(C_saver_cuda_cor_adjust, saver.cuda.handle(), t(x$estimate), t(.saver.moments(x)$se), TRUE, cor.mat)
 
 # sparse input (dgCMatrix): upload the slots once; row blocks and x.est are densified on the device.
 # In saver() (R/saver.R:156-157) and calc.estimate (R/calc_estimate.R:69) replace

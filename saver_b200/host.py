@@ -212,6 +212,41 @@ class SaverResult:
         self.cell_names = cell_names
 
 
+class LegacySaverResult:
+    """A ``saver`` object in the layout of early SAVER releases, ``list(estimate, alpha, beta,
+    info)``: the posterior of a value is Gamma(shape = alpha, rate = beta).  The reference still
+    accepts such objects in sample.saver, cor.genes, cor.cells and combine.saver
+    (R/sample_saver.R:34-36, R/cor_adjust.R:27-29,49-51, R/combine_saver.R:26-28 dispatching to
+    R/utils.R:137-232); so do the functions below, on the same device kernels."""
+
+    def __init__(self, estimate, alpha, beta, info, gene_names=None, cell_names=None):
+        self.estimate = estimate
+        self.alpha = alpha
+        self.beta = beta
+        self.info = info
+        self.gene_names = gene_names
+        self.cell_names = cell_names
+
+    def moments(self, efficiency_known=False):
+        """(mean, sd) panels that make the current kernels draw / shrink exactly as the legacy
+        code does.  Gamma mode (rgamma(alpha, beta), R/utils.R:155-156) and the correlation
+        adjustment (mean(alpha/beta^2), R/utils.R:189-191): mean = alpha/beta, sd =
+        sqrt(alpha)/beta, so shape = mean^2/sd^2 = alpha and rate = mean/sd^2 = beta.  NB mode
+        (rnbinom(mu = estimate, size = alpha), R/utils.R:152-153): mean = estimate, sd =
+        estimate/sqrt(alpha), so size = mean^2/sd^2 = alpha."""
+        a = np.asarray(self.alpha, np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if efficiency_known:
+                est = np.asarray(self.estimate, np.float64)
+                return est, est / np.sqrt(a)
+            b = np.asarray(self.beta, np.float64)
+            return a / b, np.sqrt(a) / b
+
+
+def _is_legacy(x):
+    return getattr(x, "alpha", None) is not None
+
+
 class DeviceCounts:
     """A sparse count matrix resident on the device (csrc/sparse.cu).  Replaces the Matrix-package
     calls of the reference's sparse path: colSums/rowSums (R/utils.R:72,100-115, R/saver.R:156),
@@ -575,7 +610,10 @@ def sample_saver(x, rep=1, efficiency_known=False, seed=None, handle=None, block
         raise SaverError("rep must be a positive integer.")
     if seed is None:
         seed = int(np.random.SeedSequence().generate_state(1)[0])
-    est, se = np.asarray(x.estimate), np.asarray(x.se)
+    if _is_legacy(x):  # sample.saver.old (R/utils.R:137-178)
+        est, se = x.moments(efficiency_known)
+    else:
+        est, se = np.asarray(x.estimate), np.asarray(x.se)
     outs = []
     for j in range(rep):
         out = np.empty_like(est)
@@ -587,16 +625,22 @@ def sample_saver(x, rep=1, efficiency_known=False, seed=None, handle=None, block
     return outs[0] if rep == 1 else outs
 
 
+def _posterior_sd(x):
+    """se of a current object; sqrt(alpha)/beta for a legacy one, whose adjustment uses
+    mean(alpha/beta^2) in place of mean(se^2) (cor.genes.old / cor.cells.old, R/utils.R:181-214)."""
+    return x.moments(False)[1] if _is_legacy(x) else np.asarray(x.se)
+
+
 def cor_genes(x, cor_mat=None, handle=None):
     """cor.genes (R/cor_adjust.R:26-44): gene-gene correlation of the estimates, shrunk by the
     posterior uncertainty.  The diagonal is adj^2, not 1, exactly as in the reference."""
-    return ops.cor_adjust(np.asarray(x.estimate), np.asarray(x.se), by_cells=False, cor_in=cor_mat,
+    return ops.cor_adjust(np.asarray(x.estimate), _posterior_sd(x), by_cells=False, cor_in=cor_mat,
                           handle=handle)
 
 
 def cor_cells(x, cor_mat=None, handle=None):
     """cor.cells (R/cor_adjust.R:48-66)."""
-    return ops.cor_adjust(np.asarray(x.estimate), np.asarray(x.se), by_cells=True, cor_in=cor_mat,
+    return ops.cor_adjust(np.asarray(x.estimate), _posterior_sd(x), by_cells=True, cor_in=cor_mat,
                           handle=handle)
 
 
@@ -610,6 +654,19 @@ def get_mu(x, saver_obj):
 
 def combine_saver(saver_list):
     """combine.saver (R/combine_saver.R:25-44): stack objects fitted on gene subsets."""
+    if _is_legacy(saver_list[0]):
+        # combine.saver.old (R/utils.R:217-232): rbind estimate/alpha/beta; info[[1]] (size.factor)
+        # from the first object, info[[2]] and info[[3]] concatenated, the rest from the first
+        first = saver_list[0].info
+        info = {}
+        for i, k in enumerate(first):
+            info[k] = (np.concatenate([np.atleast_1d(s.info[k]) for s in saver_list])
+                       if i in (1, 2) else first[k])
+        return LegacySaverResult(np.concatenate([s.estimate for s in saver_list], 0),
+                                 np.concatenate([s.alpha for s in saver_list], 0),
+                                 np.concatenate([s.beta for s in saver_list], 0), info,
+                                 gene_names=_cat_names([getattr(s, "gene_names", None) for s in saver_list]),
+                                 cell_names=getattr(saver_list[0], "cell_names", None))
     est = np.concatenate([s.estimate for s in saver_list], 0)
     se = np.concatenate([s.se for s in saver_list], 0)
     info = {"size.factor": saver_list[0].info["size.factor"]}
@@ -617,4 +674,12 @@ def combine_saver(saver_list):
               "lambda.coefs"):
         info[k] = np.concatenate([np.atleast_1d(s.info[k]) for s in saver_list])
     info["total.time"] = float(sum(s.info["total.time"] for s in saver_list))
-    return SaverResult(est, se, info)
+    return SaverResult(est, se, info, gene_names=_cat_names([getattr(s, "gene_names", None) for s in saver_list]),
+                       cell_names=getattr(saver_list[0], "cell_names", None))
+
+
+def _cat_names(parts):
+    """rbind keeps the row names of its arguments (None if any part has none)."""
+    if any(p is None for p in parts):
+        return None
+    return [n for p in parts for n in p]

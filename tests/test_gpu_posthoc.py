@@ -86,3 +86,26 @@ def test_get_mu_and_combine_saver(golden):
     b = saver_b200.SaverResult(obj.estimate[5:10], obj.se[5:10], info)
     c = saver_b200.combine_saver([a, b])
     assert c.estimate.shape == (10, 200) and c.info["total.time"] == 3.0 and c.info["maxcor"].size == 10
+
+
+def test_legacy_alpha_beta_objects_use_the_same_kernels(handle):
+    """sample.saver.old / cor.genes.old / cor.cells.old (R/utils.R:137-214): a legacy object
+    list(estimate, alpha, beta) must give what the current object with se = sqrt(alpha)/beta gives."""
+    rng = np.random.default_rng(4)
+    alpha = rng.gamma(3.0, 1.0, (40, 60)) + 0.05
+    beta = rng.gamma(2.0, 0.5, (40, 60)) + 0.05
+    leg = saver_b200.LegacySaverResult(alpha / beta, alpha, beta, {})
+    cur = _Obj(alpha / beta, np.sqrt(alpha) / beta, None)
+    assert np.array_equal(saver_b200.sample_saver(leg, seed=3, handle=handle),
+                          saver_b200.sample_saver(cur, seed=3, handle=handle))
+    assert np.array_equal(saver_b200.cor_genes(leg, handle=handle), saver_b200.cor_genes(cur, handle=handle))
+    assert np.array_equal(saver_b200.cor_cells(leg, handle=handle), saver_b200.cor_cells(cur, handle=handle))
+    ref = posthoc.cor_adjust(alpha / beta, np.sqrt(alpha) / beta)
+    assert np.abs(saver_b200.cor_genes(leg, handle=handle) - ref).max() < 1e-10
+    # NB mode: rnbinom(mu = estimate, size = alpha) -- mean and variance of many draws of one pair
+    a1, b1 = np.full((1, 40000), 4.5), np.full((1, 40000), 0.03)
+    k = saver_b200.sample_saver(saver_b200.LegacySaverResult(a1 / b1, a1, b1, {}), efficiency_known=True,
+                                seed=7, handle=handle)[0]
+    mu, size = 4.5 / 0.03, 4.5
+    assert abs(k.mean() - mu) < 5 * np.sqrt((mu + mu * mu / size) / k.size)
+    assert (k == np.rint(k)).all()
