@@ -1,6 +1,8 @@
 # saver_cuda.R -- the R side of the drop-in: the bodies a maintainer of mohuangx/SAVER swaps in.
 # Signatures are the reference's (NAMESPACE:3-23); everything numerical is one .Call into
-# libsaver_cuda (src/rcall_shim.c).  Untested here: the build image has no R (DESIGN.md 1b).
+# libsaver_cuda (src/rcall_shim.c).  No R in the build image (DESIGN.md 1b): the .Call sites below are
+# checked against the shim's registration table, and the shim itself runs on a fake R runtime in
+# tests/test_r_shim.py.
 
 .saver.cuda <- new.env()
 saver.cuda.handle <- function() {
