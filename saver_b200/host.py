@@ -602,25 +602,46 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
 # ----------------------------------------------------------------------------------------------
 # consumers of a saver object
 # ----------------------------------------------------------------------------------------------
-def sample_saver(x, rep=1, efficiency_known=False, seed=None, handle=None, block=4096):
+def _row_blocks(count, world):
+    """Contiguous near-equal blocks [b0, b1) of `count` rows, one per rank, and the owner vector."""
+    edges = [(count * r) // world for r in range(world + 1)]
+    owner = np.zeros(count, dtype=np.int64)
+    for r in range(world):
+        owner[edges[r]:edges[r + 1]] = r
+    return edges, owner
+
+
+def sample_saver(x, rep=1, efficiency_known=False, seed=None, handle=None, block=4096, comm=None):
     """sample.saver (R/sample_saver.R:32-79).  x: SaverResult.  Returns one (G, n) array, or a
-    list of ``rep`` arrays.  seed=None draws a fresh seed (R: the ambient RNG state)."""
+    list of ``rep`` arrays.  seed=None draws a fresh seed (R: the ambient RNG state).
+
+    With ``comm`` (one process per GPU) every rank draws a contiguous block of genes and the rows
+    are gathered; the generator is counter based on (seed, rep, gene, cell), so the dataset does
+    not depend on the number of ranks or on ``block``."""
     rep = int(rep)
     if rep <= 0:
         raise SaverError("rep must be a positive integer.")
     if seed is None:
         seed = int(np.random.SeedSequence().generate_state(1)[0])
+    world = comm.world if comm is not None else 1
+    if world > 1:
+        seed = int(comm.max_scalar(seed))  # all ranks agree on one seed
     if _is_legacy(x):  # sample.saver.old (R/utils.R:137-178)
         est, se = x.moments(efficiency_known)
     else:
         est, se = np.asarray(x.estimate), np.asarray(x.se)
+    G = est.shape[0]
+    edges, owner = _row_blocks(G, world)
+    g0, g1 = (edges[comm.rank], edges[comm.rank + 1]) if world > 1 else (0, G)
     outs = []
     for j in range(rep):
-        out = np.empty_like(est)
-        for b0 in range(0, est.shape[0], block):
-            sl = slice(b0, b0 + block)
+        out = np.zeros_like(est) if world > 1 else np.empty_like(est)
+        for b0 in range(g0, g1, block):
+            sl = slice(b0, min(b0 + block, g1))
             out[sl] = ops.sample(est[sl], se[sl], nb_mode=efficiency_known, seed=seed, rep_idx=j,
                                  gene0=b0, handle=handle)
+        if world > 1:
+            out = comm.gather_rows(out, owner)
         outs.append(out)
     return outs[0] if rep == 1 else outs
 
@@ -631,17 +652,39 @@ def _posterior_sd(x):
     return x.moments(False)[1] if _is_legacy(x) else np.asarray(x.se)
 
 
-def cor_genes(x, cor_mat=None, handle=None):
+def _cor_adjust(x, by_cells, cor_mat, handle, comm, gather):
+    est, sd = np.asarray(x.estimate), _posterior_sd(x)
+    world = comm.world if comm is not None else 1
+    if world == 1:
+        return ops.cor_adjust(est, sd, by_cells=by_cells, cor_in=cor_mat, handle=handle)
+    # every rank holds est / se and computes a block of columns of the symmetric result
+    # (cor.genes shards by column panel; the inputs are replicated)
+    M = est.shape[1] if by_cells else est.shape[0]
+    edges, owner = _row_blocks(M, world)
+    c0, c1 = edges[comm.rank], edges[comm.rank + 1]
+    cin = None if cor_mat is None else np.ascontiguousarray(np.asarray(cor_mat)[c0:c1])
+    blk = (ops.cor_adjust(est, sd, by_cells=by_cells, cor_in=cin, col0=c0, ncols=c1 - c0,
+                          handle=handle) if c1 > c0 else np.zeros((0, M)))
+    if not gather:
+        return blk, (c0, c1)
+    full = np.zeros((M, M))
+    full[c0:c1] = blk
+    return comm.gather_rows(full, owner)
+
+
+def cor_genes(x, cor_mat=None, handle=None, comm=None, gather=True):
     """cor.genes (R/cor_adjust.R:26-44): gene-gene correlation of the estimates, shrunk by the
-    posterior uncertainty.  The diagonal is adj^2, not 1, exactly as in the reference."""
-    return ops.cor_adjust(np.asarray(x.estimate), _posterior_sd(x), by_cells=False, cor_in=cor_mat,
-                          handle=handle)
+    posterior uncertainty.  The diagonal is adj^2, not 1, exactly as in the reference.
+
+    With ``comm`` each rank computes a contiguous block of columns; ``gather=False`` returns
+    ``(block, (c0, c1))`` -- rows c0..c1 of the symmetric matrix -- so that every rank can write
+    its own slice to the sink instead of materialising G x G everywhere."""
+    return _cor_adjust(x, False, cor_mat, handle, comm, gather)
 
 
-def cor_cells(x, cor_mat=None, handle=None):
-    """cor.cells (R/cor_adjust.R:48-66)."""
-    return ops.cor_adjust(np.asarray(x.estimate), _posterior_sd(x), by_cells=True, cor_in=cor_mat,
-                          handle=handle)
+def cor_cells(x, cor_mat=None, handle=None, comm=None, gather=True):
+    """cor.cells (R/cor_adjust.R:48-66); ``comm`` / ``gather`` as in cor_genes."""
+    return _cor_adjust(x, True, cor_mat, handle, comm, gather)
 
 
 def get_mu(x, saver_obj):

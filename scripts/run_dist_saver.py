@@ -14,6 +14,14 @@ if comm.rank == 0:
     same = np.array_equal(one.estimate, res.estimate) and np.array_equal(one.se, res.se)
     print("ranks", comm.world, "backend", comm.backend, "identical to one-rank run:", same,
           "max |diff|", float(np.abs(one.estimate - res.estimate).max()), flush=True)
+# the consumers of the object, sharded the same way (contiguous gene blocks / column panels)
+samp = saver_b200.sample_saver(res, seed=50, handle=h, comm=comm)
+cg = saver_b200.cor_genes(res, handle=h, comm=comm)
+if comm.rank == 0:
+    s1 = saver_b200.sample_saver(res, seed=50, handle=h)
+    c1 = saver_b200.cor_genes(res, handle=h)
+    print("sample.saver identical:", np.array_equal(s1, samp, equal_nan=True),
+          " cor.genes identical:", np.array_equal(c1, cg, equal_nan=True), flush=True)
 comm.barrier()
 import torch.distributed as _d
 _d.destroy_process_group()

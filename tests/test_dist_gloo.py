@@ -40,6 +40,95 @@ def _worker(rank, world, port, outdir):
     comm.barrier()
 
 
+class _Obj:
+    def __init__(self, est, se):
+        self.estimate, self.se = est, se
+
+
+def _cpu_posthoc_ops(ops):
+    """Stand-ins with the contract of the device ops (saver_cuda_sample: the draw depends on
+    (seed, rep, global gene, cell) only; saver_cuda_cor_adjust: column blocks of one symmetric
+    matrix), so the rank-sharded host logic can run without a GPU."""
+    from oracle import posthoc
+
+    def sample(est, se, nb_mode=False, seed=0, rep_idx=0, gene0=0, handle=None):
+        out = np.empty_like(est)
+        for g in range(est.shape[0]):
+            rng = np.random.default_rng([int(seed), int(rep_idx), int(gene0) + g, int(nb_mode)])
+            out[g] = np.round(rng.gamma(est[g] ** 2 / se[g] ** 2, se[g] ** 2 / est[g]), 3)
+        return out
+
+    def cor_adjust(est, se, by_cells=False, cor_in=None, col0=0, ncols=None, handle=None):
+        full = posthoc.cor_adjust(est, se, by_cells=by_cells)
+        ncols = full.shape[0] - col0 if ncols is None else ncols
+        blk = full[col0:col0 + ncols]
+        if cor_in is not None:  # a user-supplied cor.mat block is only rescaled
+            adj = np.sqrt(np.diag(full))
+            blk = np.asarray(cor_in) * np.outer(adj[col0:col0 + ncols], adj)
+        return blk
+
+    ops.sample, ops.cor_adjust = sample, cor_adjust
+
+
+def _posthoc_inputs():
+    rng = np.random.default_rng(12)
+    est = rng.gamma(2.0, 1.0, (13, 9)) + 0.1
+    se = rng.gamma(1.0, 0.3, (13, 9)) + 0.05
+    return est, se
+
+
+def _posthoc_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import saver_b200
+    from saver_b200 import dist, host, ops
+    _cpu_posthoc_ops(ops)
+    comm = dist.Comm(backend="gloo")
+    est, se = _posthoc_inputs()
+    obj = _Obj(est, se)
+    leg = saver_b200.LegacySaverResult(est, (est / se) ** 2, est / se ** 2, {})
+    out = {
+        "samp": host.sample_saver(obj, seed=50, comm=comm, block=4),
+        "reps": np.stack(host.sample_saver(obj, rep=2, seed=7, comm=comm)),
+        "noseed": host.sample_saver(obj, comm=comm),            # ranks must agree on one seed
+        "leg": host.sample_saver(leg, seed=50, comm=comm),
+        "cg": host.cor_genes(obj, comm=comm),
+        "cc": host.cor_cells(obj, comm=comm),
+        "cg_user": host.cor_genes(obj, cor_mat=np.corrcoef(est), comm=comm),
+    }
+    blk, (c0, c1) = host.cor_genes(obj, comm=comm, gather=False)
+    assert blk.shape == (c1 - c0, est.shape[0]) and np.array_equal(blk, out["cg"][c0:c1])
+    np.savez(os.path.join(outdir, "ph%d.npz" % rank), **out)
+    comm.barrier()
+
+
+def test_two_rank_posthoc_sharding_is_result_invariant(tmp_path):
+    """sample.saver / cor.genes / cor.cells sharded over ranks: contiguous gene
+    blocks with global gene offsets, column panels of the adjusted correlation, row gather."""
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_posthoc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from saver_b200 import host, ops
+    saved = ops.sample, ops.cor_adjust
+    try:
+        _cpu_posthoc_ops(ops)
+        est, se = _posthoc_inputs()
+        obj = _Obj(est, se)
+        one = {"samp": host.sample_saver(obj, seed=50), "reps": np.stack(host.sample_saver(obj, rep=2, seed=7)),
+               "leg": host.sample_saver(obj, seed=50), "cg": host.cor_genes(obj), "cc": host.cor_cells(obj),
+               "cg_user": host.cor_genes(obj, cor_mat=np.corrcoef(est))}
+    finally:
+        ops.sample, ops.cor_adjust = saved
+    d = [np.load(os.path.join(str(tmp_path), "ph%d.npz" % r)) for r in range(2)]
+    for k, v in one.items():
+        for r in range(2):
+            assert np.array_equal(d[r][k], v) if k in ("samp", "reps") else np.allclose(d[r][k], v, rtol=1e-12), k
+    assert np.array_equal(d[0]["noseed"], d[1]["noseed"])
+    assert one["cg"].shape == (13, 13) and one["cc"].shape == (9, 9)
+
+
 def test_two_rank_sharding_is_result_invariant(tmp_path):
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
