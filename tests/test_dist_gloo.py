@@ -100,15 +100,19 @@ def _posthoc_worker(rank, world, port, outdir):
     }
     blk, (c0, c1) = host.cor_genes(obj, comm=comm, gather=False)
     assert blk.shape == (c1 - c0, est.shape[0]) and np.array_equal(blk, out["cg"][c0:c1])
+    tiny = _Obj(est[:3], se[:3])  # fewer genes than ranks when world = 4: some blocks are empty
+    out["tiny_samp"] = host.sample_saver(tiny, seed=3, comm=comm)
+    out["tiny_cg"] = host.cor_genes(tiny, comm=comm)
     np.savez(os.path.join(outdir, "ph%d.npz" % rank), **out)
     comm.barrier()
 
 
-def test_two_rank_posthoc_sharding_is_result_invariant(tmp_path):
-    """sample.saver / cor.genes / cor.cells sharded over ranks: contiguous gene
-    blocks with global gene offsets, column panels of the adjusted correlation, row gather."""
-    port = 29900 + (os.getpid() % 90)
-    mp.spawn(_posthoc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("world", [2, 4])
+def test_posthoc_sharding_is_result_invariant(tmp_path, world):
+    """sample.saver / cor.genes / cor.cells sharded over ranks: contiguous
+    gene blocks with global gene offsets, column panels of the adjusted correlation, row gather."""
+    port = 29900 + (os.getpid() % 90) + world
+    mp.spawn(_posthoc_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from saver_b200 import host, ops
     saved = ops.sample, ops.cor_adjust
@@ -118,14 +122,17 @@ def test_two_rank_posthoc_sharding_is_result_invariant(tmp_path):
         obj = _Obj(est, se)
         one = {"samp": host.sample_saver(obj, seed=50), "reps": np.stack(host.sample_saver(obj, rep=2, seed=7)),
                "leg": host.sample_saver(obj, seed=50), "cg": host.cor_genes(obj), "cc": host.cor_cells(obj),
-               "cg_user": host.cor_genes(obj, cor_mat=np.corrcoef(est))}
+               "cg_user": host.cor_genes(obj, cor_mat=np.corrcoef(est)),
+               "tiny_samp": host.sample_saver(_Obj(est[:3], se[:3]), seed=3),
+               "tiny_cg": host.cor_genes(_Obj(est[:3], se[:3]))}
     finally:
         ops.sample, ops.cor_adjust = saved
-    d = [np.load(os.path.join(str(tmp_path), "ph%d.npz" % r)) for r in range(2)]
+    d = [np.load(os.path.join(str(tmp_path), "ph%d.npz" % r)) for r in range(world)]
     for k, v in one.items():
-        for r in range(2):
-            assert np.array_equal(d[r][k], v) if k in ("samp", "reps") else np.allclose(d[r][k], v, rtol=1e-12), k
-    assert np.array_equal(d[0]["noseed"], d[1]["noseed"])
+        for r in range(world):
+            assert (np.array_equal(d[r][k], v) if k in ("samp", "reps", "tiny_samp")
+                    else np.allclose(d[r][k], v, rtol=1e-12)), k
+    assert all(np.array_equal(d[0]["noseed"], d[r]["noseed"]) for r in range(world))
     assert one["cg"].shape == (13, 13) and one["cc"].shape == (9, 9)
 
 
