@@ -136,16 +136,45 @@ def _lm(y, x):
 # ----------------------------------------------------------------------------------------------
 # fold assignment = what cv.glmnet draws after set.seed(j) (R/expr_predict.R:35-43)
 # ----------------------------------------------------------------------------------------------
+def gene_order(perm, pred1, rest, ngenes):
+    """The processing order ``ind`` of saver.fit (R/saver_fit.R:87-92): the predictable genes in
+    random order, then the others.  perm: "identity"; an int (numpy stream); or ("R", seed) /
+    ("R-3.5", seed) -- the order the reference produces when the user calls set.seed(seed) right
+    before saver(): c(sample(pred.genes1, npred1), sample(others, ngenes - npred1)), or
+    sample(1:ngenes, ngenes) when every gene is predictable, on R's own stream with the current
+    ("Rejection", R >= 3.6) or the older ("Rounding") sampler."""
+    if isinstance(perm, str) and perm == "identity":
+        return np.concatenate([pred1, rest])
+    if isinstance(perm, (tuple, list)) and perm[0] in ("R", "R-3.5"):
+        from . import rrng
+        r = rrng.RRng(int(perm[1]), "rejection" if perm[0] == "R" else "rounding")
+        if pred1.size < ngenes:
+            return np.concatenate([r.sample(pred1), r.sample(rest)])
+        return r.sample(np.arange(ngenes))
+    rng = np.random.default_rng(perm)
+    return np.concatenate([rng.permutation(pred1), rng.permutation(rest)])
+
+
 def draw_folds(seeds, N, nfolds=5, fold_seed=0, method="philox"):
     """foldid for each gene: a permutation of rep(1..nfolds, length = N).
 
     seeds: the per-gene ``j`` of R/calc_estimate.R:98 (1-based position inside the stage block).
     method "philox": counter-based stream keyed on (fold_seed, j) -- reproducible and independent
     of how genes are split over blocks or GPUs.  (An R host draws the folds itself with
-    set.seed(j); sample(...), see INTEGRATION.md.)"""
+    set.seed(j); sample(...), see INTEGRATION.md.)
+    method "R" / "R-3.5": exactly the folds the reference draws -- set.seed(j) followed by
+    cv.glmnet's sample(rep(seq(nfolds), length = N)) -- with R's current sampler (R >= 3.6,
+    sample.kind "Rejection") or the one before it ("Rounding"); fold_seed is ignored
+    (saver_b200/rrng.py)."""
     seeds = np.asarray(seeds, dtype=np.int64)
     base = (np.arange(N) % nfolds + 1).astype(np.int32)
     out = np.empty((seeds.size, N), dtype=np.int32)
+    if method in ("R", "R-3.5"):
+        from . import rrng
+        kind = "rejection" if method == "R" else "rounding"
+        for i, j in enumerate(seeds):
+            out[i] = rrng.cv_folds(int(j), N, nfolds, kind)
+        return out
     if method != "philox":
         raise SaverError("unknown fold method %r" % (method,))
     for i, j in enumerate(seeds):
@@ -370,7 +399,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
     x (genes x cells counts), x_est ((p, n) = t(x.est) of R/saver.R:157, gene-major),
     pred_genes / pred_cells 0-based.  self_col[g]: the x_est column carrying gene g's own name or
     -1 (R/calc_estimate.R:103 compares names; indices here).
-    perm: "identity" or an int seed -- the reference permutes genes with the ambient RNG
+    perm: "identity", an int seed or ("R", seed) (gene_order) -- the reference permutes genes with the ambient RNG
     (R/saver_fit.R:87-92); the permutation only decides which genes get cross-validated in
     do.fast and the per-gene seeds."""
     msg = messages or (lambda *a: None)
@@ -402,11 +431,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
         msg("Using means as predictions.")
     st = time.time()
     rest = np.setdiff1d(np.arange(ngenes), pred1, assume_unique=False)
-    if perm == "identity":
-        ind = np.concatenate([pred1, rest])
-    else:
-        rng = np.random.default_rng(perm)
-        ind = np.concatenate([rng.permutation(pred1), rng.permutation(rest)])
+    ind = gene_order(perm, pred1, rest, ngenes)
     self_col_of = np.full(ngenes, -1, dtype=np.int32)
     if self_col is not None:
         self_col_of[:] = np.asarray(self_col, dtype=np.int32)
