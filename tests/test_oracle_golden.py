@@ -112,3 +112,69 @@ def test_cv_glue_runs_and_is_fold_dependent(golden):
         outs.append(r["idx"])
     # golden lambda.min index is 12; random folds land in its neighbourhood
     assert all(0 <= i <= 40 for i in outs)
+
+
+# ---------------------------------------------------------------------------------------------
+# T13: the cross-validation glue and R's fold draw, pinned against the stored CV results
+# ---------------------------------------------------------------------------------------------
+def _seed_scan():
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linnarsson_cv_seed_scan.npz")
+    return np.load(p)
+
+
+def _best_seed(scan, golden, target_scale=1.0):
+    """Per CV gene: the candidate seed whose folds give the stored lambda.min and the closest
+    sd.cv (relative distance to target_scale * stored sd.cv), over seeds 1..140."""
+    genes = scan["genes"]
+    gl, gs = golden["lambda_min"][genes], golden["sd_cv"][genes] * target_scale
+    same = np.abs(scan["lambda_min"] - gl[:, None]) < 1e-9 * gl[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(same, np.abs(scan["sd_cv"] / gs[:, None] - 1.0), np.inf)
+    return genes, gs, scan["j"][np.argmin(rel, 1)], rel.min(1)
+
+
+def test_t13_stored_cv_results_are_reproduced_by_r_seeded_folds(golden):
+    """The reference stored lambda.min and sd.cv of 210 cross-validated genes; each came from
+    set.seed(j); cv.glmnet(...) with j the gene's (unknown) position in its stage block, at most
+    ~132 (R/calc_estimate.R:98, R/saver_fit.R:94-163 with ncores = 12, R/saver.R:75).
+    tests/golden/find_cv_seeds.py ran the oracle's cv.glmnet restatement with R's folds
+    (saver_b200/rrng.py, R 3.5.1 sampler) for every candidate j.  If the fold stream, the fold
+    fits and the cvm / cvsd / lambda.min rules are right, most genes must have ONE candidate that
+    reproduces the stored pair -- and a wrong target must not."""
+    scan = _seed_scan()
+    done = scan["idx"][:, 0] >= 0
+    assert done.sum() >= 100
+    genes, gs, j, rel = _best_seed(scan, golden)
+    live = done & (gs > 0)          # sd.cv == 0 (lambda.min = lambda[1]) carries no information
+    hit = rel[live] < 5e-3
+    assert hit.mean() > 0.7, hit.mean()
+    assert (rel[live] < 1e-3).mean() > 0.3
+    _, _, _, rel_null = _best_seed(scan, golden, target_scale=1.37)
+    assert (rel_null[live] < 5e-3).mean() < 0.1
+    # the seeds found are positions inside three stage blocks of 12, 88 and <= 140 genes: a value
+    # can occur at most three times up to 12, twice up to 88, once above
+    conf = j[live][rel[live] < 1e-3]
+    cnt = np.bincount(conf, minlength=141)
+    assert (cnt[1:13] <= 3).all() and (cnt[13:89] <= 2).all() and (cnt[89:] <= 1).all()
+    # stage 3 holds ceil(100 / perc.pred) ~ 132 genes: the candidates above are never the match
+    assert (conf <= 134).all()
+    # a cross-validated gene whose maxcor is below the cutoff was fitted before the cutoff
+    # existed, i.e. in stage 1 or 2 (R/saver_fit.R:146-160): its seed is at most 88
+    early = live & (golden["maxcor"][genes] <= golden["cutoff"][0]) & (rel < 1e-3)
+    assert (j[early] <= 88).all()
+
+
+def test_t13_live_recheck_of_found_seeds(golden):
+    """Re-run a few (gene, seed) pairs of the committed scan with the oracle now."""
+    from saver_b200 import rrng
+    scan = _seed_scan()
+    genes, gs, j, rel = _best_seed(scan, golden)
+    order = np.argsort(rel)
+    n = golden["x"].shape[1]
+    for s in order[gs[order] > 0][:4]:
+        g = int(genes[s])
+        r = oracle.predict_cv(golden["xest"], golden["y"][g], rrng.cv_folds(int(j[s]), n, 5, "rounding"), excl=g)
+        assert _rel(r["lambda_min"], golden["lambda_min"][g]) < 1e-12
+        assert _rel(r["sd_cv"], golden["sd_cv"][g]) < 1e-3
+        assert _rel(r["sd_cv"], scan["sd_cv"][s, int(j[s]) - 1]) < 1e-12
