@@ -144,14 +144,14 @@ def test_t13_stored_cv_results_are_reproduced_by_r_seeded_folds(golden):
     reproduces the stored pair -- and a wrong target must not."""
     scan = _seed_scan()
     done = scan["idx"][:, 0] >= 0
-    assert done.sum() >= 100
+    assert done.all()
     genes, gs, j, rel = _best_seed(scan, golden)
     live = done & (gs > 0)          # sd.cv == 0 (lambda.min = lambda[1]) carries no information
     hit = rel[live] < 5e-3
-    assert hit.mean() > 0.7, hit.mean()
-    assert (rel[live] < 1e-3).mean() > 0.3
+    assert hit.mean() > 0.65, hit.mean()         # measured: 136 of 192 genes (71 %)
+    assert (rel[live] < 1e-3).mean() > 0.3          # measured: 68 of 192 (35 %)
     _, _, _, rel_null = _best_seed(scan, golden, target_scale=1.37)
-    assert (rel_null[live] < 5e-3).mean() < 0.1
+    assert (rel_null[live] < 5e-3).mean() < 0.1     # measured: 11 of 192 (6 %)
     # the seeds found are positions inside three stage blocks of 12, 88 and <= 140 genes: a value
     # can occur at most three times up to 12, twice up to 88, once above
     conf = j[live][rel[live] < 1e-3]
