@@ -29,7 +29,7 @@ def build(force=False):
         cmd = ["gcc", "-O1", "-std=gnu11", "-fPIC", "-shared", "-fvisibility=hidden"] + STRICT + \
               ["-I" + os.path.join(ROOT, "include"), "-I" + STUB] + srcs + \
               ["-o", LIB, "-L" + os.path.dirname(cuda_lib), "-lsaver_cuda",
-               "-Wl,-rpath," + os.path.dirname(cuda_lib)]
+               "-Wl,-rpath,$ORIGIN/../../saver_b200/csrc"]  # relative: the tree may be relocated
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("the .Call shim does not compile against include/saver_cuda.h:\n" + r.stderr)
@@ -44,7 +44,10 @@ class Session:
     """A fake R session: converts numpy values to SEXPs, runs .Call routines, converts back."""
 
     def __init__(self):
-        self.lib = lib = C.CDLL(build())
+        path = build()
+        from saver_b200 import build as _b
+        C.CDLL(_b.LIB, mode=C.RTLD_GLOBAL)  # resolve libsaver_cuda wherever the tree lives
+        self.lib = lib = C.CDLL(path)
         P = C.c_void_p
         lib.stub_last_error.restype = C.c_char_p
         lib.stub_routine_name.restype = C.c_char_p
