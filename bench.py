@@ -1,24 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- genes/sec of full saver() (cross-validated Poisson lasso + variance fit + posterior).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--workload cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--workload cfg3]
 
-One "step" = one pass of the whole hot path over the workload's gene block: every gene of the
-count matrix goes through calc.estimate (R/calc_estimate.R:75-141) -- 5-fold cv.glmnet Poisson
-lasso on the shared design, lambda.min prediction, calc.post -- i.e. saver(x, do.fast = FALSE,
-estimates.only = TRUE) of the reference.  Workload "cfg2" = BASELINE.json configs[1]: synthetic
-negative-binomial 5,000 genes x 2,000 cells on one B200.  With N > 1 (torchrun, one rank per
-GPU) every rank runs its own 5,000-gene block against the same design (weak scaling; genes are
-independent given the design, so there is no data-path collective).
+Default workload "cfg3" = BASELINE.json's metric: synthetic negative-binomial 20,000 genes x
+10,000 cells, do.fast = FALSE (every gene gets 5-fold cv.glmnet), estimates.only = TRUE, the full
+design (every gene with mean >= 0.1 is a predictor).  The whole matrix is hours of work, so one
+"step" = one pass of the hot path -- calc.estimate, R/calc_estimate.R:75-141: cv Poisson lasso on
+the shared design, lambda.min prediction, calc.post -- over a FIXED block of genes of that matrix
+(`--block`, evenly spaced through the predictable genes); i.e. saver(x, pred.genes = block,
+pred.genes.only = TRUE, do.fast = FALSE, estimates.only = TRUE) of the reference.  With N > 1
+(torchrun, one rank per GPU) the SAME block is dealt over the ranks (strong scaling): rank 0 holds
+x, the design goes to the other ranks with one NCCL broadcast, every rank keeps its own estimate
+rows (R/calc_estimate.R:69-74,147-160: one x, chunks over workers, x.est exported to each).
 
-Printed JSON (one line, rank 0): `value` = genes/s with all inputs resident in HBM (CUDA events on
-the library's stream, max over ranks); `e2e` = the same through saver_b200.saver() with host
-buffers (pinned), host<->device copies inside the timed region; `roofline` for the dominant
-kernel; `cpu_baseline` = the CPU oracle (oracle/, a C restatement of the reference -- R and glmnet
-cannot be installed here) on a bounded gene sample with all host threads.
+Printed JSON (one line, rank 0):
+  value     genes/s with design, counts and folds resident in HBM (CUDA events on the library's
+            stream, max over ranks, L2 flushed between steps);
+  e2e       the same through saver_b200.saver() from HOST buffers on rank 0: host preparation, H2D of
+            the design, NCCL broadcast, per-rank counts / folds H2D, D2H of each rank's estimate rows
+            all inside the timed region;
+  roofline  the prediction phase against the FP64 GEMM peak measured in this run (SURVEY.md 8(d):
+            2 n p flop per full-gradient evaluation), with the per-kernel numbers beside it;
+  cpu_baseline / parity  the CPU oracle (oracle/, a C restatement of glmnet's fishnet + cv.glmnet +
+            R's Brent; R and glmnet cannot be installed here) on a few genes of the block: its time is
+            the CPU baseline, its results are the parity check of this very run.
 
---impl reference times that CPU restatement as the reference arm (the reference itself is pure R;
-there is no R in the image).
+Other workloads: cfg2 (5,000 x 2,000, BASELINE.json configs[1]), null (saver(null.model = TRUE) on
+20,000 x 10,000: the variance-fit / posterior kernel alone), fast (do.fast = TRUE schedule on
+5,000 x 2,000), tiny.  --impl reference times the CPU restatement as the reference arm.
 """
 import argparse
 import json
@@ -27,6 +37,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -34,10 +45,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (genes, cells, seed)   -- SURVEY.md 8(d): seed = 20260 + config#
-    "cfg2": (5000, 2000, 20262),
-    "cfg3": (20000, 10000, 20263),
-    "tiny": (256, 300, 20299),
+    # name: genes, cells, seed (seed = 20260 + config#), default gene block per step
+    "cfg3": dict(G=20000, n=10000, seed=20263, block=256),
+    "cfg2": dict(G=5000, n=2000, seed=20262, block=0),      # 0 = every predictable gene
+    "tiny": dict(G=256, n=300, seed=20299, block=0),
+    "null": dict(G=20000, n=10000, seed=20263, block=0),
+    "fast": dict(G=5000, n=2000, seed=20262, block=0),
 }
 METRIC = "genes/sec, full saver() (cv Poisson lasso + variance fit + posterior), synthetic NB"
 
@@ -98,29 +111,111 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_workload(name, rank):
-    """Counts for this rank's gene block + the shared design inputs (rank 0's block)."""
+# ------------------------------------------------------------------------------------------------
+# inputs
+# ------------------------------------------------------------------------------------------------
+def make_counts(name, gene_stream=0):
     from saver_b200 import synth
-    G, n, seed = WORKLOADS[name]
-    x0 = synth.nb_counts(G, n, seed)  # the design always comes from block 0
-    x = x0 if rank == 0 else synth.nb_counts(G, n, seed, gene_stream=rank)
-    return x0, x, G, n
+    w = WORKLOADS[name]
+    return synth.nb_counts(w["G"], w["n"], w["seed"], gene_stream=gene_stream)
 
 
-def prepare(x0, x, rank):
-    """Host preprocessing exactly as saver() does it (R/saver.R:105-157)."""
+def prepare(x):
+    """Host preparation exactly as saver() does it (R/saver.R:105-157)."""
     from saver_b200 import host
-    x0c, _ = host.clean_data(x0)
-    sf, scale_sf = host.calc_size_factor(x0c, None, x0c.shape[1])
-    good = np.where(x0c.mean(1) >= 0.1)[0]
-    x_est = np.log((x0c[good] + 1.0) / sf)
-    xc = x0c if rank == 0 else np.asarray(x, dtype=np.float64)
+    xc, _ = host.clean_data(x)
+    sf, scale_sf = host.calc_size_factor(xc, None, xc.shape[1])
+    good = np.where(xc.mean(1) >= 0.1)[0]
+    x_est = np.log((xc[good] + 1.0) / sf)
     self_col = np.full(xc.shape[0], -1, dtype=np.int32)
-    if rank == 0:
-        self_col[good] = np.arange(good.size, dtype=np.int32)
-    return xc, sf, scale_sf, x_est, self_col
+    self_col[good] = np.arange(good.size, dtype=np.int32)
+    pred = np.where(xc.sum(1) > 0)[0]
+    return xc, sf, scale_sf, x_est, self_col, pred
 
 
+def pick_block(pred, block):
+    if block <= 0 or block >= pred.size:
+        return pred
+    return pred[np.linspace(0, pred.size - 1, block).astype(np.int64)]
+
+
+def stage_layout(B):
+    """Stages of saver.fit's slow schedule (R/saver_fit.R:333-462: n1 = 8, a quarter of the rest,
+    the rest) for a block of B genes in matrix order: [(start, stop)]."""
+    n1 = min(8, B)
+    n2 = min(int(np.ceil((B - n1) / 4)) + n1, B)
+    return [(a, b) for a, b in ((0, n1), (n1, n2), (n2, B)) if b > a]
+
+
+def deal(B, rank, world):
+    """Block positions this rank computes and their cv seeds j -- exactly what saver() does with the
+    block: every stage is dealt round-robin over the ranks, j = 1-based position inside the stage
+    (R/calc_estimate.R:98), so the resident arm, the e2e arm and the oracle see the same folds."""
+    pos, seeds = [], []
+    for a, b in stage_layout(B):
+        q = np.arange(a, b)[rank::world]
+        pos.append(q)
+        seeds.append(q - a + 1)
+    return np.concatenate(pos), np.concatenate(seeds)
+
+
+def counters(h):
+    from saver_b200 import ops
+    c, e = np.zeros(8), np.zeros(4)
+    h.lib.saver_cuda_counters(h.h, ops.ptr(c))
+    h.lib.saver_cuda_counters_ext(h.h, ops.ptr(e))
+    return c, e
+
+
+def fp64_gemm_peak(dev, m=6144, reps=4):
+    """cuBLAS DGEMM TF/s on this box, in this run (no FP64 figure is in MEASURED_PEAKS.json)."""
+    import torch
+    a = torch.randn(m, m, dtype=torch.float64, device=dev)
+    b = torch.randn(m, m, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2.0 * m ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    return best
+
+
+def oracle_threads():
+    cores = os.cpu_count() or 1
+    outer = 5 if cores >= 10 else 1
+    return cores, outer, max(1, cores // outer)
+
+
+def oracle_sample(x_est, xc, sf, scale_sf, self_col, genes, seeds, fold_seed, inside_gene):
+    """CPU oracle on a few genes: (seconds, dict of results).  inside_gene: threads split the column
+    loops and fold fits of ONE gene at a time (20k x 10k: a gene is minutes of scalar work);
+    otherwise one gene per thread."""
+    import oracle
+    from saver_b200 import host
+    n = xc.shape[1]
+    cores, outer, inner = oracle_threads()
+    fold = host.draw_folds(seeds, n, 5, fold_seed=fold_seed)
+    y = xc[genes] / sf
+    t0 = time.time()
+    if inside_gene:
+        oracle.set_threads(outer, inner)
+        r = oracle.predict_cv_batch(x_est, y, fold, self_col=self_col[genes], threads=1)
+        oracle.set_threads(1, 1)
+    else:
+        r = oracle.predict_cv_batch(x_est, y, fold, self_col=self_col[genes], threads=cores)
+    post = oracle.calc_post_batch(xc[genes], r["mu"], sf, scale_sf, threads=cores)
+    return time.time() - t0, dict(est=post["est"], idx=r["idx"], lmin=r["lambda_min"], rc=r["rc"])
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
 def run_cuda(args):
     import torch
     import saver_b200
@@ -131,53 +226,86 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (libsaver_cuda has no CPU fallback)")
     torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl")
-    h = saver_b200.Handle(local)
-    x0, x, G, n = make_workload(args.workload, rank)
-    xc, sf, scale_sf, x_est, self_col = prepare(x0, x, rank)
-    p = x_est.shape[0]
     dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        from saver_b200 import dist as sdist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=dev)
+        comm = sdist.Comm(init=False)
+    h = saver_b200.Handle(local)
     stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+    w = WORKLOADS[args.workload]
+    n = w["n"]
+    block = w["block"] if args.block is None else args.block
 
-    # ---------------- resident arm: everything already in HBM ----------------
-    ops.set_design(x_est, handle=h)
-    rs = xc.sum(1)
-    pred = np.where(rs > 0)[0]
-    seeds = np.arange(1, pred.size + 1)
+    def barrier():
+        h.synchronize()
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
+
+    # ---------------- inputs: rank 0 holds the matrix ----------------
+    t_setup = time.time()
+    x_host = xc = x_est = None
+    if rank == 0:
+        x_host = make_counts(args.workload, args.gene_stream)
+        xc, sf, scale_sf, x_est, self_col, pred = prepare(x_host)
+        genes = pick_block(pred, block)
+        plan = dict(sf=sf, scale_sf=scale_sf, genes=genes, self_col=self_col[genes], p=x_est.shape[0])
+    else:
+        plan = None
+    if comm is not None:
+        plan = comm.bcast_obj(plan)
+    sf, scale_sf, genes, p = plan["sf"], plan["scale_sf"], plan["genes"], plan["p"]
+    B = genes.size
+    mine, seeds = deal(B, rank, world)
+    # resident arm set-up (untimed): design upload + one NCCL broadcast, the block's counts
+    bc_ms = None
+    if comm is not None:
+        xd = torch.from_numpy(x_est).to(dev) if rank == 0 else None
+        comm.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        xd = comm.broadcast_array(xd, keep_on_device=True)
+        e1.record()
+        torch.cuda.synchronize()
+        bc_ms = e0.elapsed_time(e1)
+        ops.set_design(xd, handle=h)
+        del xd
+        xblk = comm.broadcast_array(xc[genes] if rank == 0 else None)
+    else:
+        ops.set_design(x_est, handle=h)
+        xblk = xc[genes]
+    h.synchronize()
     fold_h = host.draw_folds(seeds, n, 5, fold_seed=args.fold_seed)
-    Xd = torch.from_numpy(np.ascontiguousarray(xc[pred])).to(dev)
+    Xd = torch.from_numpy(np.ascontiguousarray(xblk[mine])).to(dev)
     sfd = torch.from_numpy(sf).to(dev)
-    scd = torch.from_numpy(self_col[pred]).to(dev)
+    scd = torch.from_numpy(np.ascontiguousarray(plan["self_col"][mine])).to(dev)
     fold_d = torch.from_numpy(fold_h).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dgemm_tf = fp64_gemm_peak(dev) if rank == 0 else None
     torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
 
     def resident_step():
+        if mine.size == 0:
+            return None
         return ops.calc_estimate(Xd, sfd, scale_sf, 1, self_col=scd, foldid=fold_d, nfolds=5,
                                  calc_maxcor=False, want_se=False, handle=h)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        h.synchronize()
-
+    # ---------------- resident arm ----------------
     for _ in range(args.warmup):
         flush.zero_()
         resident_step()
     barrier()
-    c0 = np.zeros(8)
-    h.lib.saver_cuda_counters(h.h, ops.ptr(c0))
-    ext0 = np.zeros(4)
-    h.lib.saver_cuda_counters_ext(h.h, ops.ptr(ext0))
+    c0, ext0 = counters(h)
     clocks = ClockSampler(local)
     clocks.start()
     evs = []
     t_host0 = time.time()
+    out = None
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
@@ -189,158 +317,217 @@ def run_cuda(args):
     barrier()
     t_host = time.time() - t_host0
     clk = clocks.stop()
-    c1 = np.zeros(8)
-    h.lib.saver_cuda_counters(h.h, ops.ptr(c1))
-    ext1 = np.zeros(4)
-    h.lib.saver_cuda_counters_ext(h.h, ops.ptr(ext1))
+    c1, ext1 = counters(h)
     ms = sum(a.elapsed_time(b) for a, b in evs)
     dc = c1 - c0
-    ngenes_step = pred.size
-    # ---------------- e2e arm: the public API with host buffers ----------------
-    x_pin = torch.from_numpy(np.ascontiguousarray(xc)).pin_memory().numpy()
-    e2e_t = []
-    h2d = xc.nbytes + x_est.nbytes + fold_h.nbytes + sf.nbytes + self_col.nbytes
-    d2h = xc.nbytes
-    if args.no_e2e:
-        e2e_t = [float("nan")]
-    else:
-        # one small pass warms the host-buffer path (pinned staging, allocator), then the timed pass
-        saver_b200.saver(x_pin[:64], do_fast=False, estimates_only=True, fold_seed=args.fold_seed,
-                         backend=host.CudaBackend(handle=h))
-        for it in range(args.e2e_steps):
+    est_res = out["est"].cpu().numpy() if out is not None else np.zeros((0, n))
+    status_res = out["status"].cpu().numpy() if out is not None else np.zeros(0, dtype=np.int32)
+    lmin_res = out["lambda_min"].cpu().numpy() if out is not None else np.zeros(0)
+
+    # ---------------- e2e arm: the public API, host buffers on rank 0 ----------------
+    e2e_t, h2d, d2h, nvl = [], 0, 0, 0
+    e2e_est = None
+    if not args.no_e2e:
+        be = host.CudaBackend(handle=h, comm=comm)
+        kw = dict(do_fast=False, estimates_only=True, fold_seed=args.fold_seed, perm="identity",
+                  pred_genes_only=True, backend=be, comm=comm, gather=False)
+        x_pin = None
+        if rank == 0:
+            x_pin = torch.from_numpy(np.ascontiguousarray(x_host)).pin_memory().numpy()
+        for it in range(args.e2e_steps + 1):   # the first pass warms the host-buffer path
+            nv0 = comm.bytes_broadcast if comm is not None else 0
             barrier()
             t0 = time.time()
-            est = saver_b200.saver(x_pin, do_fast=False, estimates_only=True,
-                                   fold_seed=args.fold_seed, backend=host.CudaBackend(handle=h))
+            res = saver_b200.saver(x_pin, pred_genes=genes if it else genes[:max(2 * world, 4)], **kw)
             h.synchronize()
-            e2e_t.append(time.time() - t0)
-            assert np.isfinite(est).all()
-            d2h = est.nbytes
-    e2e_s = float(np.mean(e2e_t))
+            dt = time.time() - t0
+            if it:
+                e2e_t.append(dt)
+                own = np.where(res.owner == rank)[0]
+                e2e_est = res.estimate[own]
+                assert np.isfinite(e2e_est).all()
+                d2h = e2e_est.nbytes
+                nvl = (comm.bytes_broadcast - nv0) if comm is not None else 0
+                # H2D on this rank: the design (rank 0 only), its genes' counts and folds, sf, self_col
+                h2d = (p * n * 8 if rank == 0 else 0) + own.size * n * (8 + 4) + n * 8 + own.size * 4
+    e2e_s = float(np.mean(e2e_t)) if e2e_t else float("nan")
 
-    tmax = ms / 1e3
-    e2e_max = e2e_s
-    if dist is not None:
+    tmax, e2e_max = ms / 1e3, e2e_s
+    sums = np.array([dc[0], dc[1], dc[2], dc[3], dc[5], dc[7], float(h2d), float(d2h)])
+    if comm is not None:
         t = torch.tensor([tmax, e2e_max], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         tmax, e2e_max = float(t[0]), float(t[1])
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        s = torch.from_numpy(sums).to(dev)
+        tdist.all_reduce(s)
+        sums = s.cpu().numpy()
+        nranks_seen = int(comm.max_scalar(world))
     if rank != 0:
+        if comm is not None:
+            comm.barrier()
+            tdist.destroy_process_group()
         return
-    total_genes = ngenes_step * world * args.steps
-    value = total_genes / tmax
+
+    # ---------------- parity sample + CPU baseline (rank 0, outside every timed region) ----------
+    parity, cpu = None, None
+    k = args.parity if args.parity is not None else (0 if (world > 1 or args.no_cpu) else
+                                                     (2 if n >= 5000 else 2 * (os.cpu_count() or 1)))
+    k = min(k, mine.size)
+    if k > 0:
+        sel = np.linspace(0, mine.size - 1, k).astype(int)
+        inside = n >= 5000
+        dt, ref = oracle_sample(x_est, xc, sf, scale_sf, self_col, genes[mine[sel]], seeds[sel],
+                                args.fold_seed, inside)
+        got = est_res[sel]
+        rel = np.abs(got - ref["est"]) / np.maximum(ref["est"], 1e-12)
+        parity = {"genes": int(k), "median_rel_err_estimate": float(np.median(rel)),
+                  "per_gene_median_rel_err": [float(v) for v in np.median(rel, 1)][:16],
+                  "lambda_min_equal": int(np.isclose(ref["lmin"], lmin_res[sel], rtol=1e-9, atol=0).sum()),
+                  "status_equal": int((ref["rc"] == status_res[sel]).sum()),
+                  "tolerance": "median <= 1e-3 (north_star)", "ok": bool(np.median(rel) <= 1e-3),
+                  "against": "oracle/saver_oracle.c on the same genes and folds, outside the timed region"}
+        if e2e_est is not None and world == 1:   # same genes, same folds: the e2e result is checked too
+            rel2 = np.abs(e2e_est[mine[sel]] - ref["est"]) / np.maximum(ref["est"], 1e-12)
+            parity["e2e_median_rel_err_estimate"] = float(np.median(rel2))
+        cores, outer, inner = oracle_threads()
+        cpu = {"value": k / dt, "unit": "genes/s", "cores": cores, "kind": "port",
+               "sample": "%d genes of the block, full design, %.1f s%s" % (
+                   k, dt, " (threads inside a gene: %d fold fits x %d column threads)" % (outer, inner)
+                   if inside else " (one gene per thread)"),
+               "note": "oracle/saver_oracle.c (glmnet-style IRLS + coordinate descent, R's Brent); the "
+                       "reference itself is R + glmnet, not installable in this image"}
+
+    # ---------------- the line ----------------
     hbm, which = peaks()
-    # dominant kernel: the lasso round kernel.  Its algorithmic HBM-side work is the design columns
-    # it streams (n x 8 B each, counted in-kernel); its FP64 tensor work is the Gram blocks (DMMA).
-    gram_flops = 2.0 * (ext1[2] - ext0[2])
-    col_bytes = dc[4] * n * 8.0
-    round_s = dc[0] / 1e3
-    gemm_s = dc[1] / 1e3
-    gemm_flops = dc[5] * 2.0 * n * p
-    kname = "lasso_round_gram_kernel" if os.environ.get("SAVER_LASSO_GRAM", "1") != "0" else "lasso_round_kernel"
-    # DRAM bytes of one launch of that kernel from the committed ncu --set full capture
-    traffic, tnote = None, ""
-    tp = os.path.join(ROOT, "profiles", "r1b_round_kernel_traffic.json")
-    if kname == "lasso_round_gram_kernel" and os.path.exists(tp):
+    round_s, gemm_s, setup_s, post_s, gemm_cols, launches = (sums[0] / 1e3, sums[1] / 1e3, sums[2] / 1e3,
+                                                              sums[3] / 1e3, sums[4], sums[5])
+    genes_done = B * args.steps
+    value = genes_done / tmax
+    pred_flops = 2.0 * n * p * gemm_cols                  # 2 n p per gradient evaluation
+    pred_busy = round_s + gemm_s + setup_s                # GPU-seconds summed over ranks
+    pred_tf = pred_flops / pred_busy / 1e12 if pred_busy > 0 else None
+    traffic, tnote = None, None
+    tp = os.path.join(ROOT, "profiles", "r2_round_kernel_traffic.json")
+    if os.path.exists(tp):
         td = json.load(open(tp))
-        traffic = td["dram_bytes_per_launch"]
-        tnote = (" traffic = dram read + write of the captured launch (%s); the same launch moved %.0f GB "
-                 "from L2 to the SMs" % (td["capture"], td["l2_to_sm_bytes_per_launch"] / 1e9))
-    roof = {"kernel": kname, "bound": "hbm",
-            "achieved": col_bytes / round_s / 1e9 if round_s > 0 else None, "peak": hbm,
-            "unit": "GB/s", "frac": (col_bytes / round_s / 1e9 / hbm) if round_s > 0 else None,
-            "traffic": traffic, "peak_source": which,
-            "note": "algorithmic bytes = design columns streamed x n x 8 B (counted in-kernel) over the "
-                    "CUDA-event time of the round kernels; the columns are served by L2 (80% hits), the "
-                    "kernel is latency bound (profiles/README.md)." + tnote,
-            "gram_dmma_tflops_inside_kernel": gram_flops / round_s / 1e12 if round_s > 0 else None,
-            "share_of_step": {kname: round_s / tmax, "gemm_tn_f64_kernel": gemm_s / tmax,
-                              "lasso_setup": dc[2] / 1e3 / tmax, "calc_post_kernel": dc[3] / 1e3 / tmax},
-            "gemm": {"bound": "fp64-mma", "achieved_tflops": gemm_flops / gemm_s / 1e12 if gemm_s > 0 else None,
-                     "flops_per_column": 2.0 * n * p,
-                     "note": "no FP64 peak in MEASURED_PEAKS.json; cuBLAS DGEMM measured 36 TF/s on these shapes"}}
+        traffic, tnote = td.get("dram_bytes_per_launch"), td.get("capture")
+    post_bytes = 24.0 * n * genes_done                   # read y, mu + write est (estimates.only)
+    roof = {
+        "kernel": "prediction phase = lasso_round_gram_kernel + gemm_tn_f64_kernel",
+        "bound": "tensor", "unit": "TFLOP/s",
+        "achieved": pred_tf, "peak": dgemm_tf, "frac": pred_tf / dgemm_tf if pred_tf and dgemm_tf else None,
+        "peak_source": "cuBLAS DGEMM %d^3 via torch.matmul, measured in this run" % 6144,
+        "traffic": traffic, "traffic_source": tnote,
+        "algorithmic": "2*n*p flop per full-gradient evaluation x %.0f evaluations/gene "
+                       "(floor (F+1)*L_g)" % (gemm_cols / max(genes_done, 1)),
+        "share_of_gpu_time": {"lasso_round_gram_kernel": round_s / max(pred_busy + post_s, 1e-9),
+                              "gemm_tn_f64_kernel": gemm_s / max(pred_busy + post_s, 1e-9),
+                              "lasso_setup": setup_s / max(pred_busy + post_s, 1e-9),
+                              "calc_post_kernel": post_s / max(pred_busy + post_s, 1e-9)},
+        "kernels": {
+            "gemm_tn_f64_kernel": {"bound": "tensor", "unit": "TFLOP/s",
+                                   "achieved": pred_flops / gemm_s / 1e12 if gemm_s > 0 else None,
+                                   "peak": dgemm_tf,
+                                   "frac": pred_flops / gemm_s / 1e12 / dgemm_tf if gemm_s > 0 and dgemm_tf else None},
+            "calc_post_kernel": {"bound": "hbm", "unit": "GB/s",
+                                 "achieved": post_bytes / post_s / 1e9 if post_s > 0 else None,
+                                 "peak": hbm, "peak_source": which,
+                                 "frac": post_bytes / post_s / 1e9 / hbm if post_s > 0 else None,
+                                 "algorithmic": "24*n B/gene (estimates.only); the kernel is FP64-"
+                                                "transcendental bound, see profiles/"},
+        },
+    }
     line = {
         "metric": METRIC, "value": value, "unit": "genes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tmax * 1e3 / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: synthetic negative-binomial %d genes x %d cells per GPU, "
-                               "do.fast=FALSE (5-fold cv.glmnet Poisson lasso for every gene), "
-                               "estimates.only=TRUE, %d predictors" % (args.workload, G, n, p),
-                   "genes_per_step_per_gpu": int(ngenes_step), "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": "gene-sharded x%d, no data-path collective" % world},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, w, B, p),
+                   "genes_per_step": int(B), "genes_per_step_per_gpu": int(np.ceil(B / world)),
+                   "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": "one gene block dealt round-robin over %d rank(s); design = one NCCL "
+                                  "broadcast; no data-path collective" % world},
         "clocks": clk,
-        "e2e": {"value": ngenes_step * world / e2e_max, "unit": "genes/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "api": "saver_b200.saver(x, do_fast=False, estimates_only=True)",
+        "e2e": {"value": B / e2e_max if e2e_max == e2e_max else None, "unit": "genes/s",
+                "h2d_bytes_per_step": int(sums[6]), "d2h_bytes_per_step": int(sums[7]),
+                "nvlink_bytes_per_step": int(nvl) * max(world - 1, 0),
+                "api": "saver_b200.saver(x on rank 0, pred_genes=block, pred_genes_only=True, "
+                       "do_fast=False, estimates_only=True, gather=False)",
                 "s_per_step": e2e_max},
-        "gpu_launches": int(dc[7]),
+        "gpu_launches": int(launches),
         "roofline": roof,
-        "host_s_timed_region": t_host,
+        "fp64_gemm_peak_tflops": dgemm_tf,
+        "design_broadcast": None if bc_ms is None else {"ms": bc_ms, "bytes": int(p) * n * 8,
+                                                        "GBps": p * n * 8 / bc_ms / 1e6},
+        "comm_nranks_seen": nranks_seen if comm is not None else 1,
+        "status_counts": np.bincount(status_res, minlength=3).tolist(),
+        "host_s_timed_region": t_host, "setup_s": t_setup,
     }
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(xc, sf, scale_sf, x_est, self_col, pred, fold_h, args)
+    if parity is not None:
+        line["parity"] = parity
+    if cpu is not None and world == 1:
+        line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.barrier()
+        tdist.destroy_process_group()
 
 
-def cpu_baseline(xc, sf, scale_sf, x_est, self_col, pred, fold_h, args, budget_genes=None):
-    """The CPU oracle (C restatement of glmnet's fishnet + cv glue + R's Brent) on a bounded gene
-    sample of the same workload, all host threads."""
-    import oracle
-    cores = os.cpu_count() or 1
-    k = budget_genes or max(cores, 8)
-    sel = np.linspace(0, pred.size - 1, k).astype(int)
-    g = pred[sel]
-    y = xc[g] / sf
-    t0 = time.time()
-    r = oracle.predict_cv_batch(x_est, y, fold_h[sel], self_col=self_col[g], threads=cores)
-    oracle.calc_post_batch(xc[g], r["mu"], sf, scale_sf, threads=cores)
-    dt = time.time() - t0
-    return {"value": k / dt, "unit": "genes/s", "cores": cores, "kind": "port",
-            "sample": "%d genes of the same block (evenly spaced), full design, %.1f s" % (k, dt),
-            "note": "oracle/saver_oracle.c (glmnet-style IRLS + coordinate descent, R's Brent); the "
-                    "reference itself is R + glmnet, not installable in this image"}
+def workload_name(name, w, B, p):
+    return ("%s: synthetic negative-binomial %d genes x %d cells, do.fast=FALSE (5-fold cv.glmnet "
+            "Poisson lasso for every gene of the step's block), estimates.only=TRUE, %d predictors, "
+            "%d genes per step" % (name, w["G"], w["n"], p, B))
 
 
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the CPU restatement on the host cores
+# ------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    import oracle
     from saver_b200 import host
-    x0, x, G, n = make_workload(args.workload, 0)
-    xc, sf, scale_sf, x_est, self_col = prepare(x0, x, 0)
-    pred = np.where(xc.sum(1) > 0)[0]
-    cores = os.cpu_count() or 1
-    k = max(cores, 4)  # the oracle runs one gene per thread: a step keeps every host thread busy
-    times = []
-    last = None
-    for it in range(args.warmup + args.steps):
-        sel = np.linspace(it, pred.size - 1 - (args.warmup + args.steps - it), k).astype(int)
-        fold = host.draw_folds(sel + 1, n, 5, fold_seed=args.fold_seed)
-        import oracle
-        t0 = time.time()
-        g = pred[sel]
-        r = oracle.predict_cv_batch(x_est, xc[g] / sf, fold, self_col=self_col[g], threads=cores)
-        oracle.calc_post_batch(xc[g], r["mu"], sf, scale_sf, threads=cores)
-        dt = time.time() - t0
+    w = WORKLOADS[args.workload]
+    n = w["n"]
+    block = w["block"] if args.block is None else args.block
+    x_host = make_counts(args.workload, args.gene_stream)
+    xc, sf, scale_sf, x_est, self_col, pred = prepare(x_host)
+    genes = pick_block(pred, block)
+    B, p = genes.size, x_est.shape[0]
+    cores, outer, inner = oracle_threads()
+    inside = n >= 5000
+    nsteps = args.warmup + args.steps
+    times, done = [], []
+    last = 0.0
+    if inside:
+        # one gene per step would be minutes: a step = the genes that fit ~10 s on this box, with the
+        # threads working INSIDE a gene (5 fold fits at a time x column threads)
+        per_step = max(1, args.ref_genes)
+        sample = "%d gene(s) of the block per step, threads inside the gene (%d fold fits x %d column threads)" % (
+            per_step, outer, inner)
+    else:
+        per_step = 2 * cores
+        sample = "%d genes of the block per step, one gene per thread (dynamic)" % per_step
+    for it in range(nsteps):
+        sel = (np.arange(per_step) * max(1, B // (per_step * nsteps)) + it * per_step) % B
+        mine, seeds = deal(B, 0, 1)
+        dt, _ = oracle_sample(x_est, xc, sf, scale_sf, self_col, genes[sel], seeds[np.searchsorted(mine, sel)],
+                              args.fold_seed, inside)
         if it >= args.warmup:
             times.append(dt)
+            done.append(sel.size)
         last = dt
     tot = float(np.sum(times))
-    value = k * len(times) / tot
-    p = x_est.shape[0]
+    value = float(np.sum(done)) / tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "genes/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot * 1e3 / max(len(times), 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "%s: synthetic negative-binomial %d genes x %d cells per GPU, "
-                               "do.fast=FALSE (5-fold cv.glmnet Poisson lasso for every gene), "
-                               "estimates.only=TRUE, %d predictors" % (args.workload, G, n, p)},
+        "config": {"workload": workload_name(args.workload, w, B, p)},
         "cpu_baseline": {"value": value, "unit": "genes/s", "cores": cores, "kind": "port",
-                         "sample": "%d genes per step (evenly spaced through the block), full design; "
-                                   "last step %.1f s" % (k, last)},
+                         "sample": sample + "; last step %.1f s" % last},
         "e2e": {"value": value, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference path (oracle/saver_oracle.c) on all host threads; "
                 "the reference is R + glmnet (Fortran) and neither is installable here (DESIGN.md)",
@@ -354,16 +541,38 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--block", type=int, default=None, help="genes per step (default: the workload's)")
+    ap.add_argument("--gene-stream", type=int, default=0,
+                    help="draw another block of genes over the same cells (synth.nb_counts)")
     ap.add_argument("--fold-seed", type=int, default=5)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--parity", type=int, default=None, help="genes checked against the CPU oracle")
+    ap.add_argument("--ref-genes", type=int, default=1, help="genes per step of the reference arm (large n)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) arm")
     ap.add_argument("--e2e-steps", type=int, default=1)
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_cuda(args)
+    try:
+        if args.workload in ("null", "fast") and args.impl == "cuda":
+            import bench_extra
+            bench_extra.run(args)
+        elif args.impl == "reference":
+            run_reference(args)
+        else:
+            run_cuda(args)
+    except BaseException:
+        # torchrun swallows a rank's traceback: print it (and the library's last error is part of
+        # the exception text) before the non-zero exit
+        sys.stderr.write("[bench.py rank %s] failed:\n%s\n" % (os.environ.get("RANK", "0"),
+                                                                traceback.format_exc()))
+        sys.stderr.flush()
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "bench_rank%s.err" % os.environ.get("RANK", "0")), "w") as f:
+                f.write(traceback.format_exc())
+        except OSError:
+            pass
+        raise
 
 
 if __name__ == "__main__":

@@ -27,6 +27,9 @@ calc.estimate <- function(x, x.est, cutoff = 0, coefs = NULL, sf, scale.sf, pred
                           pred.cells, null.model, nworkers, calc.maxcor, estimates.only) {
   h <- saver.cuda.handle()
   x <- as.matrix(x)
+  storage.mode(x) <- "double"                       # integer count matrices are common
+  storage.mode(x.est) <- "double"
+  if (is.null(rownames(x))) rownames(x) <- seq_len(nrow(x))   # clean.data's default names
   if (!identical(.saver.cuda$design, x.est)) {      # x.est is installed once per saver() call
     .Call(C_saver_cuda_set_design, h, x.est)
     .saver.cuda$design <- x.est
@@ -63,8 +66,12 @@ calc.loglik.k <- function(k, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.ha
 # replaces R/calc_maxcor.R:26-42
 calc.maxcor <- function(x1, x2) {
   h <- saver.cuda.handle()
+  storage.mode(x1) <- "double"
+  storage.mode(x2) <- "double"
   .Call(C_saver_cuda_set_design, h, x1)
-  self.col <- match(colnames(x2), colnames(x1), nomatch = 0L) - 1L
+  .saver.cuda$design <- x1                          # the resident design changed: keep the cache honest
+  self.col <- if (is.null(colnames(x2)) || is.null(colnames(x1))) rep(-1L, ncol(x2))
+              else match(colnames(x2), colnames(x1), nomatch = 0L) - 1L
   .Call(C_saver_cuda_maxcor, h, x2, as.integer(self.col))
 }
 

@@ -32,6 +32,25 @@ static void check(saver_cuda_handle h, int rc)
     if (rc != SAVER_OK) Rf_error("libsaver_cuda error %d: %s", rc, saver_cuda_last_error(h));
 }
 
+/* Argument checks run BEFORE the library call: REAL()/INTEGER() on a value of another type, or a
+ * vector shorter than the library will read, must become an R error, never an out-of-bounds read
+ * (len < 0: any length; NULL is accepted only where the caller tests Rf_isNull first). */
+static double *real_arg(SEXP x, R_xlen_t len, const char *what)
+{
+    if (!Rf_isReal(x)) Rf_error("libsaver_cuda: %s must be a double vector / matrix (use storage.mode<-)", what);
+    if (len >= 0 && (R_xlen_t)Rf_length(x) != len)
+        Rf_error("libsaver_cuda: %s has length %d, expected %ld", what, Rf_length(x), (long)len);
+    return REAL(x);
+}
+
+static int *int_arg(SEXP x, R_xlen_t len, const char *what)
+{
+    if (!Rf_isInteger(x)) Rf_error("libsaver_cuda: %s must be an integer vector", what);
+    if (len >= 0 && (R_xlen_t)Rf_length(x) != len)
+        Rf_error("libsaver_cuda: %s has length %d, expected %ld", what, Rf_length(x), (long)len);
+    return INTEGER(x);
+}
+
 SEXP C_saver_cuda_create(SEXP device)
 {
     saver_cuda_handle h = NULL;
@@ -47,7 +66,8 @@ SEXP C_saver_cuda_create(SEXP device)
 SEXP C_saver_cuda_set_design(SEXP hp, SEXP xest)
 {
     saver_cuda_handle h = get_handle(hp);
-    check(h, saver_cuda_set_design(h, REAL(xest), Rf_nrows(xest), Rf_ncols(xest), 0));
+    check(h, saver_cuda_set_design(h, real_arg(xest, (R_xlen_t)Rf_nrows(xest) * Rf_ncols(xest), "x.est"),
+                                   Rf_nrows(xest), Rf_ncols(xest), 0));
     return R_NilValue;
 }
 
@@ -59,14 +79,19 @@ SEXP C_saver_cuda_calc_estimate(SEXP hp, SEXP xt, SEXP sf, SEXP scale_sf, SEXP s
 {
     saver_cuda_handle h = get_handle(hp);
     const int n = Rf_nrows(xt), B = Rf_ncols(xt), eo = Rf_asLogical(estimates_only);
+    const R_xlen_t nb = (R_xlen_t)n * B;
+    double *px = real_arg(xt, nb, "t(x)"), *psf = real_arg(sf, n, "sf");
+    int *pself = int_arg(self_col, B, "self.col"), *ppred = int_arg(is_pred, B, "is.pred");
+    int *pmask = Rf_isNull(pred_mask) ? NULL : int_arg(pred_mask, n, "pred.cells mask");
+    int *pfold = Rf_isNull(foldid) ? NULL : int_arg(foldid, nb, "foldid");
+    double *pcoefs = Rf_isNull(coefs) ? NULL : real_arg(coefs, 2, "coefs");
     SEXP est = PROTECT(Rf_allocMatrix(REALSXP, n, B));
     SEXP se = PROTECT(eo ? Rf_ScalarLogical(NA_LOGICAL) : Rf_allocMatrix(REALSXP, n, B));
     SEXP info = PROTECT(Rf_allocMatrix(REALSXP, B, 6));
     int rc = saver_cuda_calc_estimate(
-        h, REAL(xt), n, B, REAL(sf), Rf_asReal(scale_sf), INTEGER(self_col), INTEGER(is_pred),
-        Rf_isNull(pred_mask) ? NULL : INTEGER(pred_mask), Rf_isNull(foldid) ? NULL : INTEGER(foldid),
+        h, px, n, B, psf, Rf_asReal(scale_sf), pself, ppred, pmask, pfold,
         5, Rf_asInteger(mode), Rf_asLogical(calc_maxcor), Rf_asReal(cutoff),
-        Rf_isNull(coefs) ? NULL : REAL(coefs), 300, 100, 1e-7, REAL(est), eo ? NULL : REAL(se),
+        pcoefs, 300, 100, 1e-7, REAL(est), eo ? NULL : REAL(se),
         REAL(info), NULL, NULL, 0);
     check(h, rc);
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
@@ -82,8 +107,10 @@ SEXP C_saver_cuda_calc_post(SEXP hp, SEXP y, SEXP mu, SEXP sf, SEXP scale_sf)
 {
     saver_cuda_handle h = get_handle(hp);
     const int n = Rf_length(y);
+    double *py = real_arg(y, n, "y"), *pmu = real_arg(mu, Rf_length(mu) == 1 ? 1 : n, "mu"),
+           *psf = real_arg(sf, n, "sf");
     SEXP est = PROTECT(Rf_allocVector(REALSXP, n)), se = PROTECT(Rf_allocVector(REALSXP, n));
-    check(h, saver_cuda_calc_post(h, REAL(y), REAL(mu), Rf_length(mu) == 1, REAL(sf), n, 1,
+    check(h, saver_cuda_calc_post(h, py, pmu, Rf_length(mu) == 1, psf, n, 1,
                                   Rf_asReal(scale_sf), REAL(est), REAL(se), NULL, NULL, NULL, NULL, 0));
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
     SET_VECTOR_ELT(out, 0, est);
@@ -96,10 +123,13 @@ SEXP C_saver_cuda_calc_post(SEXP hp, SEXP y, SEXP mu, SEXP sf, SEXP scale_sf)
 SEXP C_saver_cuda_calc_var(SEXP hp, SEXP model, SEXP y, SEXP mu, SEXP sf)
 {
     saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_length(y);
+    double *py = real_arg(y, n, "y"), *pmu = real_arg(mu, Rf_length(mu) == 1 ? 1 : n, "mu"),
+           *psf = real_arg(sf, Rf_length(sf) == 1 ? 1 : n, "sf");
     SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
     int flags = 0;
-    check(h, saver_cuda_calc_var(h, Rf_asInteger(model), REAL(y), REAL(mu), Rf_length(mu), REAL(sf),
-                                 Rf_length(sf), Rf_length(y), REAL(out), &flags, NULL));
+    check(h, saver_cuda_calc_var(h, Rf_asInteger(model), py, pmu, Rf_length(mu), psf,
+                                 Rf_length(sf), n, REAL(out), &flags, NULL));
     UNPROTECT(1);
     return out;
 }
@@ -108,8 +138,11 @@ SEXP C_saver_cuda_loglik(SEXP hp, SEXP model, SEXP param, SEXP y, SEXP mu, SEXP 
 {
     saver_cuda_handle h = get_handle(hp);
     double v = 0;
-    check(h, saver_cuda_loglik(h, Rf_asInteger(model), Rf_asReal(param), REAL(y), REAL(mu),
-                               Rf_length(mu), REAL(sf), Rf_length(sf), Rf_length(y), &v));
+    const int n = Rf_length(y);
+    double *py = real_arg(y, n, "y"), *pmu = real_arg(mu, Rf_length(mu) == 1 ? 1 : n, "mu"),
+           *psf = real_arg(sf, Rf_length(sf) == 1 ? 1 : n, "sf");
+    check(h, saver_cuda_loglik(h, Rf_asInteger(model), Rf_asReal(param), py, pmu,
+                               Rf_length(mu), psf, Rf_length(sf), n, &v));
     return Rf_ScalarReal(v);
 }
 
@@ -117,8 +150,11 @@ SEXP C_saver_cuda_loglik(SEXP hp, SEXP model, SEXP param, SEXP y, SEXP mu, SEXP 
 SEXP C_saver_cuda_maxcor(SEXP hp, SEXP yt, SEXP self_col)
 {
     saver_cuda_handle h = get_handle(hp);
-    SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_ncols(yt)));
-    check(h, saver_cuda_maxcor(h, REAL(yt), Rf_ncols(yt), INTEGER(self_col), REAL(out), 0));
+    const int B = Rf_ncols(yt);
+    double *py = real_arg(yt, (R_xlen_t)Rf_nrows(yt) * B, "x2");
+    int *pself = int_arg(self_col, B, "self.col");
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, B));
+    check(h, saver_cuda_maxcor(h, py, B, pself, REAL(out), 0));
     UNPROTECT(1);
     return out;
 }
@@ -128,8 +164,9 @@ SEXP C_saver_cuda_sample(SEXP hp, SEXP est_t, SEXP se_t, SEXP nb, SEXP seed, SEX
 {
     saver_cuda_handle h = get_handle(hp);
     const int n = Rf_nrows(est_t), G = Rf_ncols(est_t);
+    double *pe = real_arg(est_t, (R_xlen_t)n * G, "t(estimate)"), *ps = real_arg(se_t, (R_xlen_t)n * G, "t(se)");
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, G));
-    check(h, saver_cuda_sample(h, REAL(est_t), REAL(se_t), n, G, 0, Rf_asLogical(nb),
+    check(h, saver_cuda_sample(h, pe, ps, n, G, 0, Rf_asLogical(nb),
                                (unsigned long long)Rf_asReal(seed), Rf_asInteger(rep), REAL(out), 0));
     UNPROTECT(1);
     return out;
@@ -140,9 +177,10 @@ SEXP C_saver_cuda_cor_adjust(SEXP hp, SEXP est_t, SEXP se_t, SEXP by_cells, SEXP
     saver_cuda_handle h = get_handle(hp);
     const int n = Rf_nrows(est_t), G = Rf_ncols(est_t), bc = Rf_asLogical(by_cells);
     const int M = bc ? n : G;
+    double *pe = real_arg(est_t, (R_xlen_t)n * G, "t(estimate)"), *ps = real_arg(se_t, (R_xlen_t)n * G, "t(se)");
+    double *pc = Rf_isNull(cor_mat) ? NULL : real_arg(cor_mat, (R_xlen_t)M * M, "cor.mat");
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, M, M));
-    check(h, saver_cuda_cor_adjust(h, REAL(est_t), REAL(se_t), n, G, bc,
-                                   Rf_isNull(cor_mat) ? NULL : REAL(cor_mat), 0, M, REAL(out), 0));
+    check(h, saver_cuda_cor_adjust(h, pe, ps, n, G, bc, pc, 0, M, REAL(out), 0));
     UNPROTECT(1);
     return out;
 }
@@ -152,8 +190,9 @@ SEXP C_saver_cuda_cor_adjust(SEXP hp, SEXP est_t, SEXP se_t, SEXP by_cells, SEXP
 SEXP C_saver_cuda_set_counts_csc(SEXP hp, SEXP p, SEXP i, SEXP xv, SEXP dim)
 {
     saver_cuda_handle h = get_handle(hp);
-    check(h, saver_cuda_set_counts_csc(h, INTEGER(p), INTEGER(i), REAL(xv), INTEGER(dim)[0],
-                                       INTEGER(dim)[1]));
+    int *pd = int_arg(dim, 2, "dim"), *pp = int_arg(p, (R_xlen_t)pd[1] + 1, "x@p");
+    const R_xlen_t nnz = pp[pd[1]];
+    check(h, saver_cuda_set_counts_csc(h, pp, int_arg(i, nnz, "x@i"), real_arg(xv, nnz, "x@x"), pd[0], pd[1]));
     return R_NilValue;
 }
 
@@ -161,8 +200,9 @@ SEXP C_saver_cuda_csc_sums(SEXP hp, SEXP dim)
 {
     saver_cuda_handle h = get_handle(hp);
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
-    SEXP cs = PROTECT(Rf_allocVector(REALSXP, INTEGER(dim)[1]));
-    SEXP rs = PROTECT(Rf_allocVector(REALSXP, INTEGER(dim)[0]));
+    int *pd = int_arg(dim, 2, "dim");
+    SEXP cs = PROTECT(Rf_allocVector(REALSXP, pd[1]));
+    SEXP rs = PROTECT(Rf_allocVector(REALSXP, pd[0]));
     check(h, saver_cuda_csc_sums(h, REAL(cs), REAL(rs)));
     SET_VECTOR_ELT(out, 0, cs);
     SET_VECTOR_ELT(out, 1, rs);
@@ -175,9 +215,10 @@ SEXP C_saver_cuda_csc_gather(SEXP hp, SEXP genes0, SEXP sf, SEXP ncells)
 {
     saver_cuda_handle h = get_handle(hp);
     const int B = Rf_length(genes0), n = Rf_asInteger(ncells);
+    int *pg = int_arg(genes0, B, "genes");
+    double *psf = Rf_isNull(sf) ? NULL : real_arg(sf, n, "sf");
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, B));
-    check(h, saver_cuda_csc_gather(h, INTEGER(genes0), B, Rf_isNull(sf) ? NULL : REAL(sf),
-                                   !Rf_isNull(sf), REAL(out), 0));
+    check(h, saver_cuda_csc_gather(h, pg, B, psf, psf != NULL, REAL(out), 0));
     UNPROTECT(1);
     return out;
 }

@@ -44,6 +44,12 @@ def lib():
     return _lib
 
 
+def set_threads(outer=1, inner=1):
+    """Host threads INSIDE one gene (see saver_oracle.c: orc_set_threads): `outer` fold fits at a
+    time, each splitting its column loops over `inner` threads.  Results do not change."""
+    lib().orc_set_threads(int(outer), int(inner))
+
+
 def _d(a):
     return None if a is None else a.ctypes.data_as(_dp)
 

@@ -40,8 +40,32 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ORC_API __attribute__((visibility("default")))
+
+/*
+ * Host threads INSIDE one gene (bench.py's CPU arm at the 20k x 10k shape, where one gene is
+ * minutes of scalar work): the loops over predictor columns that dominate glmnet's cost (per-fit
+ * standardisation, the full-gradient / KKT passes, the curvature pass over the strong set) are
+ * split over `orc_inner_threads` threads, and the nfolds fold fits of cv.glmnet run on
+ * `orc_outer_threads` teams at once.  Every column is still reduced by ONE thread in the original
+ * order, so results are bit-identical to the single-threaded run (tests/test_oracle_golden.py).
+ * Default 1 x 1: the callers that map genes over a thread pool keep one gene per thread.
+ */
+static int orc_outer_threads = 1, orc_inner_threads = 1;
+static _Thread_local int tl_threads = 0; /* threads of the fit running on this thread (0: inner) */
+static int fit_threads(void) { return tl_threads > 0 ? tl_threads : orc_inner_threads; }
+ORC_API void orc_set_threads(int outer, int inner)
+{
+    orc_outer_threads = outer > 1 ? outer : 1;
+    orc_inner_threads = inner > 1 ? inner : 1;
+#ifdef _OPENMP
+    omp_set_max_active_levels(2);
+#endif
+}
 
 typedef long double ld;
 
@@ -549,6 +573,9 @@ static void fishnet1(int m, int p, const double *xs, const int *ju, const double
     int nin = 0, nlp = 0, mnl = mnlam < nlam ? mnlam : nlam;
     const double shr = thr * dvr;
     double al = 0.0;
+    const int nth = fit_threads();
+    (void)nth;
+#pragma omp parallel for schedule(static) num_threads(nth) if (nth > 1 && (size_t)p * m > 4000000)
     for (int j = 0; j < p; ++j) {
         if (!ju[j]) continue;
         const double *xj = xs + (size_t)j * m;
@@ -573,6 +600,7 @@ static void fishnet1(int m, int p, const double *xs, const int *ju, const double
         for (;;) { /* IRLS outer loop */
             double az0 = az;
             for (int l = 0; l < nin; ++l) as[ia[l]] = a[ia[l]];
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nth) if (nth > 1 && (size_t)p * m > 4000000)
             for (int j = 0; j < p; ++j) {
                 if (!ixx[j]) continue;
                 const double *xj = xs + (size_t)j * m;
@@ -655,6 +683,7 @@ static void fishnet1(int m, int p, const double *xs, const int *ju, const double
             if (changed) continue;
             fi->ngrad++;
             int viol = 0;
+#pragma omp parallel for schedule(static) num_threads(nth) reduction(| : viol) if (nth > 1 && (size_t)p * m > 4000000)
             for (int k = 0; k < p; ++k) {
                 if (ixx[k] || !ju[k]) continue;
                 const double *xk = xs + (size_t)k * m;
@@ -733,6 +762,9 @@ static void glmnet_poisson(const double *x, int n_all, int p, const int *rows, i
     double *y = (double *)malloc(sizeof(double) * m);
     for (int i = 0; i < m; ++i) y[i] = y_all[rows[i]];
     const double q = 1.0 / m;
+    const int nth = fit_threads();
+    (void)nth;
+#pragma omp parallel for schedule(static) num_threads(nth) if (nth > 1 && (size_t)p * m > 4000000)
     for (int j = 0; j < p; ++j) {
         const double *xj = x + (size_t)j * n_all;
         double *sj = xs + (size_t)j * m;
@@ -826,42 +858,60 @@ ORC_API int orc_predict_cv(const double *x, int n, int p, const double *y, const
     double lam[NL], a0[NL], dev[NL];
     double *beta = (double *)malloc(sizeof(double) * (size_t)p * NL);
     glm_info gi;
+    tl_threads = orc_outer_threads * orc_inner_threads; /* the master fit runs alone: all threads */
     glmnet_poisson(x, n, p, rows, m, y, excl, NULL, 0, dfmax, thr, 100000, lam, a0, beta, dev, &gi);
+    tl_threads = 0;
     int L = gi.lmu, tot_nlp = gi.nlp, tot_gr = gi.ngrad;
     if (gi.jerr > 0 || L < 1) { free(beta); fill_mean(y, rows, m, n, mu); return 2; }
     /* fold fits on the master lambda sequence */
     double *cvraw = (double *)calloc((size_t)nfolds * L, sizeof(double)); /* per-fold mean deviance */
     double *nf = (double *)calloc(nfolds, sizeof(double));
-    double *fbeta = (double *)malloc(sizeof(double) * (size_t)p * L);
-    int *tr = (int *)malloc(sizeof(int) * m), *te = (int *)malloc(sizeof(int) * m);
-    double flam[NL], fa0[NL], fdev[NL];
     int bad = 0;
-    for (int fo = 1; fo <= nfolds && !bad; ++fo) {
+    const int nouter = orc_outer_threads < nfolds ? orc_outer_threads : nfolds;
+    (void)nouter;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nouter) if (nouter > 1)
+    for (int fo = 1; fo <= nfolds; ++fo) {
+        double *fbeta = (double *)malloc(sizeof(double) * (size_t)p * L);
+        int *tr = (int *)malloc(sizeof(int) * m), *te = (int *)malloc(sizeof(int) * m);
+        double flam[NL], fa0[NL], fdev[NL];
         int ntr = 0, nte = 0;
         for (int i = 0; i < m; ++i) {
             if (foldid[i] == fo) te[nte++] = rows[i]; else tr[ntr++] = rows[i];
         }
         glm_info fg;
+        tl_threads = nouter > 1 ? orc_inner_threads : orc_outer_threads * orc_inner_threads;
         glmnet_poisson(x, n, p, tr, ntr, y, excl, lam, L, dfmax, thr, 100000, flam, fa0, fbeta, fdev,
                        &fg);
-        tot_nlp += fg.nlp; tot_gr += fg.ngrad;
-        if (fg.jerr > 0 || fg.lmu < 1) { bad = 1; break; }
-        nf[fo - 1] = nte;
-        for (int l = 0; l < L; ++l) {
-            int ls = l < fg.lmu ? l : fg.lmu - 1; /* short fold path: last column repeated */
-            const double *bl = fbeta + (size_t)ls * p;
-            ld acc = 0;
-            for (int i = 0; i < nte; ++i) {
-                int r = te[i];
-                double eta = fa0[ls];
-                for (int j = 0; j < p; ++j) if (bl[j] != 0.0) eta += x[(size_t)j * n + r] * bl[j];
-                double yy = y[r];
-                double deveta = yy * eta - exp(eta);
-                double devy = yy == 0 ? 0 : yy * log(yy) - yy;
-                acc += 2 * (devy - deveta);
+        tl_threads = 0;
+#pragma omp atomic
+        tot_nlp += fg.nlp;
+#pragma omp atomic
+        tot_gr += fg.ngrad;
+        if (fg.jerr > 0 || fg.lmu < 1) {
+#pragma omp atomic write
+            bad = 1;
+        } else {
+            nf[fo - 1] = nte;
+            const int nth = nouter > 1 ? orc_inner_threads : orc_outer_threads * orc_inner_threads;
+            (void)nth;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nth) if (nth > 1 && (size_t)p * m > 4000000)
+            for (int l = 0; l < L; ++l) {
+                int ls = l < fg.lmu ? l : fg.lmu - 1; /* short fold path: last column repeated */
+                const double *bl = fbeta + (size_t)ls * p;
+                ld acc = 0;
+                for (int i = 0; i < nte; ++i) {
+                    int r = te[i];
+                    double eta = fa0[ls];
+                    for (int j = 0; j < p; ++j) if (bl[j] != 0.0) eta += x[(size_t)j * n + r] * bl[j];
+                    double yy = y[r];
+                    double deveta = yy * eta - exp(eta);
+                    double devy = yy == 0 ? 0 : yy * log(yy) - yy;
+                    acc += 2 * (devy - deveta);
+                }
+                cvraw[(size_t)(fo - 1) * L + l] = (double)(acc / nte);
             }
-            cvraw[(size_t)(fo - 1) * L + l] = (double)(acc / nte);
         }
+        free(fbeta); free(tr); free(te);
     }
     int rc = 0;
     if (bad) { fill_mean(y, rows, m, n, mu); rc = 2; }
@@ -898,7 +948,7 @@ ORC_API int orc_predict_cv(const double *x, int n, int p, const double *y, const
         }
     }
     if (stats) { stats[0] = L; stats[1] = gi.jerr; stats[2] = tot_nlp; stats[3] = tot_gr; }
-    free(beta); free(cvraw); free(nf); free(fbeta); free(tr); free(te);
+    free(beta); free(cvraw); free(nf);
     return rc;
 }
 

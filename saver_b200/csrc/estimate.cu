@@ -146,6 +146,13 @@ extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, in
   if (mode == 1 && (!foldid || nfolds < 3 || nfolds > kMaxFolds))
     return fail(h, SAVER_ERR_ARG, "calc_estimate: CV needs foldid and 3 <= nfolds <= 16");
   if (mode == 2 && !coefs) return fail(h, SAVER_ERR_ARG, "calc_estimate: fixed-lambda needs coefs");
+  // same limits as saver_cuda_predict_cv: the lambda tables hold kNLam entries, the ever-active list
+  // kNX (glmnet's pmax = 2 * dfmax + 20 must fit, otherwise the path would truncate differently)
+  if (mode != 0 && (nlambda < 1 || nlambda > kNLam || dfmax < 1 || 2 * (long long)dfmax + 20 > kNX ||
+                    !(thresh > 0)))
+    return fail(h, SAVER_ERR_ARG,
+                "calc_estimate: need 1 <= nlambda <= %d, 1 <= dfmax <= %d, thresh > 0 (got %d, %d, %g)",
+                kNLam, (kNX - 20) / 2, nlambda, dfmax, thresh);
   if (B == 0) return SAVER_OK;
   CU(cudaSetDevice(h->device));
   const bool dev = device_ptrs != 0;
@@ -283,7 +290,7 @@ extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, in
         prm.alf_wide = prm.alf_tall = 1.0;
       }
       CU(cudaGetLastError());
-      const int chunk = lasso_max_block(prm.NF, D);
+      const int chunk = lasso_max_block(prm.NF, D, h->lasso.tune);
       for (int b0 = 0; b0 < Bp; b0 += chunk) {
         prm.B = Bp - b0 < chunk ? Bp - b0 : chunk;
         CU(lasso_run(D, h->lasso, prm, Yp.p + n * b0, dFoldP.p + n * b0, dSelfP.p + b0,

@@ -37,9 +37,25 @@
 
 namespace saver {
 
+void LassoTuning::from_env() {
+  auto geti = [](const char* k, int& v) { if (const char* e = getenv(k)) v = atoi(e); };
+  geti("SAVER_LASSO_PROBLEMS", problems);
+  geti("SAVER_LASSO_DBG", dbg);
+  geti("SAVER_LASSO_GRAM", gram);
+  geti("SAVER_LASSO_THREADS", threads);
+  geti("SAVER_GRAM_THREADS", gram_threads);
+  geti("SAVER_GRAM_CTAS", gram_ctas);
+  geti("SAVER_GRAM_STAGED", gram_staged);
+  geti("SAVER_L2_PERSIST", l2_persist);
+  if (const char* e = getenv("SAVER_GRAM_HS")) gram_hs = atol(e);
+  if (const char* e = getenv("SAVER_STRONG_SLACK")) strong_slack = atof(e);
+}
+
 void LassoWs::release() {
   if (base) cudaFree(base);
   if (h_counter) cudaFreeHost(h_counter);
+  if (h_crumb) cudaFreeHost(h_crumb);
+  h_crumb = d_crumb = nullptr;
   for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
   base = nullptr;
   h_counter = nullptr;
@@ -61,6 +77,7 @@ struct RoundArgs {
   const int* fold;    // n x B: 0 = not a pred cell, 1..nfolds (path variant: any non-zero)
   const int* self;    // B or null
   int mh;             // largest active set whose packed Gram block fits the shared-memory region
+  int round_no;       // round index of this launch (breadcrumbs)
   LassoWs ws;
 };
 
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(256) lasso_setup_kernel(RoundArgs A) {
   if (tid == 0) {
     LassoProb pr;
     pr.gene = g; pr.fit = fit; pr.state = ST_INIT; pr.lidx = 0; pr.lmu = 0; pr.nin = 0; pr.nS = 0;
-    pr.jerr = 0; pr.nlp = 0; pr.ngrad = 0; pr.mtrain = mtrain; pr.slot = pid; pr.resumed = 0;
+    pr.jerr = 0; pr.nlp = 0; pr.ngrad = 0; pr.mtrain = mtrain; pr.slot = pid;
     pr.al = 0; pr.al0 = 0; pr.qv = qv; pr.yb = yb;
     pr.az = 0; pr.dv0 = 0; pr.dvr = 0; pr.shr = 0; pr.v0 = yb; pr.sumr = 0;
     pr.cur_dev = 0; pr.cur_cv = 0; pr.ncv = v3[1];
@@ -1009,84 +1026,8 @@ __device__ __noinline__ double2 rows_comb(const double* __restrict__ Xi, size_t 
   return make_double2(s0, s1);
 }
 
-// One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane).  The
-// Hessian column of step t+NB is pulled into L1 with prefetch.global.L1 while step t runs (no
-// registers are tied up, so nothing spills behind the load), the column of step t is then an L1
-// hit issued at the top of the step; the reciprocal of the curvature is formed one step ahead.
-// Results (dlx, q0, changed flag) go through `gsh`.
-template <int Q, int NB>
-__device__ __noinline__ void gram_sweep_warp(const double* H, int ldh, int m, bool by_index,
-                                             const int* ord, double* gq, const double* va,
-                                             const double* vinv, double* aact, const double* swa,
-                                             double al, double* gsh, double dlx, double q0) {
-  const int lane = threadIdx.x & 31;
-  double qr[Q];
-#pragma unroll
-  for (int e = 0; e < Q; ++e) {
-    const int j = lane + 32 * e;
-    qr[e] = j < m ? gq[j] : 0.0;
-  }
-  auto pf = [&](int t) {  // one prefetch per 32-byte sector of the column of step t
-    if (t < m && (lane & 3) == 0) {
-      const int l = by_index ? ord[t] : t;
-#pragma unroll
-      for (int e = 0; e < Q; ++e) {
-        const int j = lane + 32 * e;
-        if (j < m) prefetch_l1(H + j + (size_t)l * ldh);
-      }
-    }
-  };
-#pragma unroll
-  for (int b = 0; b < NB; ++b) pf(b);
-  bool dty = false, bad = false;
-  int ln = by_index ? ord[0] : 0;
-  double vn = va[ln], an = aact[ln], sn = swa[ln], rn = vinv[ln];
-  for (int t = 0; t < m && !bad; ++t) {
-    const int l = ln;
-    const double v = vn, ak = an, sw = sn, rv = rn;
-    double hc[Q];
-#pragma unroll
-    for (int e = 0; e < Q; ++e) {
-      const int j = lane + 32 * e;
-      hc[e] = j < m ? H[j + (size_t)l * ldh] : 0.0;
-    }
-    pf(t + NB);
-    if (t + 1 < m) {
-      ln = by_index ? ord[t + 1] : t + 1;
-      vn = va[ln]; an = aact[ln]; sn = swa[ln]; rn = vinv[ln];
-    }
-    double sel = qr[0];
-    const int qi = l >> 5;
-#pragma unroll
-    for (int e = 1; e < Q; ++e) sel = qi == e ? qr[e] : sel;
-    const double ql = __shfl_sync(0xffffffffu, sel, l & 31);
-    const double u = ql + v * ak;
-    const double au = fabs(u) - al;
-    // glmnet: sign(au, u) / v ; the reciprocal differs from the division by <= 1 ulp
-    const double anew = au > 0.0 ? (u > 0.0 ? au : -au) * rv : 0.0;
-    if (anew == ak) continue;
-    if (anew != anew) { bad = true; break; }
-    const double d = anew - ak;
-    dlx = fmax(dlx, v * d * d);
-#pragma unroll
-    for (int e = 0; e < Q; ++e) qr[e] -= d * hc[e];
-    q0 -= d * sw;
-    if (lane == 0) aact[l] = anew;
-    dty = true;
-  }
-#pragma unroll
-  for (int e = 0; e < Q; ++e) {
-    const int j = lane + 32 * e;
-    if (j < m) gq[j] = qr[e];
-  }
-  if (lane == 0) {
-    gsh[0] = bad ? NAN : dlx;
-    gsh[1] = q0;
-    gsh[2] = dty ? 1.0 : 0.0;
-  }
-}
-
-// The same sweep with the Gram block in shared memory, packed lower-triangular by rows
+// One Gram-space sweep executed by a single warp: q lives in registers (Q entries per lane), the
+// Gram block in shared memory, packed lower-triangular by rows
 // (element (r, c), r >= c, at r(r+1)/2 + c).  Column l seen by lane j is the contiguous run
 // l(l+1)/2 + j for j <= l and the triangular-stride run j(j+1)/2 + l below it; triangular numbers
 // visit every residue mod 16 exactly twice per 32 lanes, so both halves are bank-conflict free.
@@ -1097,8 +1038,7 @@ __device__ __noinline__ void gram_sweep_warp(const double* H, int ldh, int m, bo
 // ALU ops on the sign word -> DMUL (new coefficient) -> select -> DADD (d) -> DFMA (q update).
 // Nothing branches on the chain (d = 0 makes every update an exact no-op), everything else of
 // step t+1 -- scalars, the Gram column, the index -- is loaded while step t's chain drains, and in
-// natural order the shuffle source register is static.  Same arithmetic, same results as
-// gram_sweep_warp.
+// natural order the shuffle source register is static.
 struct SweepAcc {
   double dlx, q0;
   unsigned dty, bad;
@@ -1347,6 +1287,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     if (timing) { const long long t = clock64(); tph[k] += t - tmark; tmark = t; }
   };
   int ninact = 0;
+  int* crumb_p = (A.prm.dbg & 4096) && A.ws.d_crumb ? A.ws.d_crumb + (size_t)(blockIdx.x % kCrumbSlots) * 8 : nullptr;
   // The list is in completion order of the previous round (quick problems first); taking it from
   // the back starts the long-running problems first, so the round does not end on stragglers.
   const int lpos = (A.prm.dbg & 2048) ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
@@ -1357,8 +1298,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   const int g = PR->gene, fit = PR->fit, slot = PR->slot;
   int state = PR->state, lidx = PR->lidx, lmu = PR->lmu, nin = PR->nin, nS = PR->nS;
   int jerr = PR->jerr, nlp = PR->nlp;
-  bool force_irls = PR->resumed != 0;  // resumed mid-solve: the next outer check cannot be the last
-  bool yielded = false, yielded_mid = false;  // gave up the time slice (mid: inside an IRLS step)
   double al = PR->al, al0 = PR->al0, az = PR->az, v0 = PR->v0, sumr = PR->sumr;
   double cur_dev = PR->cur_dev, cur_cv = PR->cur_cv;
   const double qv = PR->qv, dv0 = PR->dv0, dvr = PR->dvr, shr = PR->shr, ncv = PR->ncv;
@@ -1388,6 +1327,16 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   const bool is_fold = fit > 0;
   const int maxit = A.prm.maxit;
   const double fmax_ = log(DBL_MAX * 0.1);
+  int crumb_m = 0;
+  auto crumb = [&](int tag) {
+    if (crumb_p && tid == 0) {
+      volatile int* c = crumb_p;
+      c[0] = A.round_no; c[1] = pid; c[2] = tag; c[3] = lidx; c[4] = nin; c[5] = nS; c[6] = crumb_m;
+      c[7] = ninact;
+      __threadfence_system();
+    }
+  };
+  crumb(1);
 
   if (!STAGED) {
     wv = Wg;
@@ -1533,6 +1482,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // design; the n-space residual is only materialised before the strong-set check of the inactive
   // variables (batched dots, no per-variable barrier) and when a variable enters.
   lap(0);
+  crumb(2);
   double* H = nullptr;
   int hslot = -1;
   if (state == ST_SOLVE) {
@@ -1677,9 +1627,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         else if (m <= 128) gram_sweep_sm<4>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
         else if (m <= 192) gram_sweep_sm<6>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
         else gram_sweep_sm<8>(Hsm, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
-      } else if (A.prm.dbg & 1024) {  // the first Gram-space sweep (A/B reference)
-        if (m <= 128) gram_sweep_warp<4, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
-        else gram_sweep_warp<8, 4>(H, ldh, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
       } else if (m <= 64) gram_sweep_g<2>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
       else if (m <= 128) gram_sweep_g<4>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
       else if (m <= 192) gram_sweep_g<6>(H, m, by_index, ord, gq, va, gq2, aact, swa, al, gsh, dlx, q0);
@@ -1748,7 +1695,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     tph[8] += m;
     tph[9] += 1;
     if (timing && tid == 0) atomicAdd(A.ws.phasecyc + 16 + (m - 1) / 32, (unsigned long long)m);
-    if (m <= ((A.prm.dbg & 1024) ? 256 : 384)) gsweep_warp(by_index, m, dlx);
+    if (m <= 384) gsweep_warp(by_index, m, dlx);
     else gsweep_block(by_index, m, dlx);
   };
   auto gintercept = [&](int m, double& dlx) {
@@ -1802,6 +1749,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   };
   // a strong-set variable enters: n-space coordinate update + one new Gram row/column
   auto activate = [&](int k, double xm, double xi, double gk, int& m, double& dlx) -> bool {
+    crumb_m = m;
+    crumb(7);
     const double* col = Xs + (size_t)k * ldx;
     double d2[2] = {0.0, 0.0};
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
@@ -1987,15 +1936,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     }
   };
 
-  // Time slice.  A round ends when its slowest problem does, and a few (gene, lambda) pairs need
-  // thousands of sweeps (glmnet's maxit is 1e5): such a problem gives up the SM after its slice,
-  // leaves a consistent n-space state (coefficients, intercept, w, wr materialised) and continues
-  // in the next round from state ST_SOLVE, while the other problems move on to their next lambda.
-  const long long slice = A.prm.slice_cycles;
-  auto slice_over = [&]() -> bool {
-    return slice > 0 && __syncthreads_or(tid == 0 && clock64() - t_start > slice);
-  };
-
   if (state == ST_SOLVE) {
     // inactive members of the strong set, in index order
     {
@@ -2068,13 +2008,19 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       }
       tph[7] += 1;
       tph[12] += m;
+      crumb_m = m;
+      crumb(4);
       while (true) {  // strong-set phases until one changes nothing
         ++nlp;
         double dlx = 0.0;
         if (!(dbg & 2)) gsweep(true, m, dlx);
         lap(3);
         lap(4);
+        crumb_m = m;
+        crumb(6);
         if (!(dbg & 8)) inactive_check(m, dlx, overflow);
+        crumb_m = m;
+        crumb(5);
         lap(5);
         if (overflow) break;
         gintercept(m, dlx);
@@ -2090,7 +2036,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
           if (dlx < shr) break;
           if (!(dlx == dlx)) { nanfail = true; break; }
           if (nlp > maxit) { maxed = true; break; }
-          if ((inner & 7) == 7 && slice_over()) { yielded = true; break; }
           if (++inner >= 64 && !H_fresh && m > 0) {
             // A model that mixes weights of several IRLS steps (kept block + rows of variables that
             // entered later) is not guaranteed to be a Gram matrix; if the sweeps stall, rebuild it
@@ -2107,14 +2052,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             inner = 0;
           }
         }
-        if (maxed || nanfail || yielded) break;
-        if (slice_over()) { yielded = true; break; }
-      }
-      if (yielded) {  // n-space state of the current iterate; the solve resumes next round
-        materialise(m);
-        sumr = q0;
-        yielded_mid = true;
-        break;
+        if (maxed || nanfail) break;
       }
       if (overflow) { jerr = -10000 - (lidx + 1); state = ST_DONE; break; }
       if (maxed) { jerr = -(lidx + 1); state = ST_DONE; break; }
@@ -2122,6 +2060,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
 
       // ---- re-linearise: f = az + sum_l a_l x~_l, w = q exp(f), wr = t - w ----
       lap(3);
+      crumb(8);
       __syncthreads();
       double c0p[1] = {0.0};
       for (int l = tid; l < nin; l += T) {
@@ -2187,18 +2126,16 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         bad |= va[l] * d * d >= shr;
       }
       lap(6);
-      if (force_irls) bad = 1;
-      force_irls = false;
       if (!__syncthreads_or(bad)) {
         state = ST_WAIT_KKT;
         break;
       }
-      if (slice_over()) { yielded = true; break; }  // w, wr are the fresh linearisation: nothing to save
     }
   }
 
   // ---------------- write back ----------------
   __syncthreads();
+  crumb(9);
   if (STAGED) {
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
       __stcs(reinterpret_cast<double2*>(Wg + i), *reinterpret_cast<const double2*>(wv + i));
@@ -2236,10 +2173,11 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     atomicAdd(A.ws.colcount + 3, (unsigned long long)(state == ST_WAIT_KKT || state == ST_DONE));
     if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
     PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
-    PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1; PR->resumed = yielded_mid ? 1 : 0;
+    PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
     PR->al = al; PR->al0 = al0; PR->az = az; PR->v0 = v0; PR->sumr = sumr;
     PR->cur_dev = cur_dev; PR->cur_cv = cur_cv;
   }
+  crumb(10);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2448,11 +2386,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-int lasso_max_block(int NF, const DesignState& D) {
+int lasso_max_block(int NF, const DesignState& D, const LassoTuning& tune) {
   // problems in flight per block: enough waves that a round does not end on a part-filled one
   // (12,288 = 41 waves of 296 resident CTAs), bounded by a third of the free device memory
   int tot = 12288;
-  if (const char* e = getenv("SAVER_LASSO_PROBLEMS")) tot = atoi(e);
+  if (tune.problems > 0) tot = tune.problems;
   const double per_problem = (double)D.ldx * 8 * 3 + (double)D.p_pad * (8 * 3 + 4 * 3) + (double)kNX * 28;
   const double per_gene = NF * per_problem + (double)kNLam * (kNX * 8 + kMaxFolds * 8 + 32);
   size_t free_b = 0, total_b = 0;
@@ -2521,15 +2459,15 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   RoundArgs A;
   A.Xs = D.Xs; A.xsd = D.xsd; A.n = n; A.ldx = ldx; A.p = D.p; A.p_pad = p_pad; A.P = P;
   A.prm = prm;
-  if (const char* e = getenv("SAVER_LASSO_DBG")) A.prm.dbg = atoi(e);
-  if (const char* e = getenv("SAVER_STRONG_SLACK")) A.prm.strong_slack = atof(e);
-  // Time slices are opt-in (SAVER_SLICE_CYCLES=<cycles>; 15,000 x n was the setting measured on
-  // do.fast): with that default the cross-validated auto-lambda path died with an "illegal
-  // instruction" on the device (tests/test_gpu_saver.py full-cv case and the bench workload), so
-  // the default stays 0 = a problem runs its lambda to the end, the configuration every committed
-  // number was measured with.
-  A.prm.slice_cycles = 0;
-  if (const char* e = getenv("SAVER_SLICE_CYCLES")) A.prm.slice_cycles = atoll(e);
+  const LassoTuning& tune = ws.tune;
+  if (tune.dbg >= 0) A.prm.dbg = tune.dbg;
+  if (tune.strong_slack >= 0) A.prm.strong_slack = tune.strong_slack;
+  if ((A.prm.dbg & 4096) && !ws.h_crumb) {
+    if ((e = cudaHostAlloc(&ws.h_crumb, (size_t)kCrumbSlots * 32, cudaHostAllocMapped)) != cudaSuccess) return e;
+    memset(ws.h_crumb, 0, (size_t)kCrumbSlots * 32);
+    if ((e = cudaHostGetDevicePointer(&ws.d_crumb, ws.h_crumb, 0)) != cudaSuccess) return e;
+  }
+  A.round_no = 0;
   A.Yn = Yn; A.fold = fold; A.self = self; A.ws = ws;
 
   if ((e = cudaMemsetAsync(ws.counters, 0, 64, s)) != cudaSuccess) return e;
@@ -2566,27 +2504,27 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   const int mode = smem_x <= 113 * 1024 ? 2 : smem_s <= 227 * 1024 ? 1 : 0;
   const size_t smem = mode == 2 ? smem_x : mode == 1 ? smem_s : kFixedSmem;
   bool gram = prm.gram != 0;
-  if (const char* e = getenv("SAVER_LASSO_GRAM")) gram = atoi(e) != 0;
+  if (tune.gram >= 0) gram = tune.gram != 0;
   int T = ldx <= 2048 ? 128 : ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
   if (gram) T = ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
-  if (gram) if (const char* e = getenv("SAVER_GRAM_THREADS")) T = atoi(e);
-  if (const char* e = getenv("SAVER_LASSO_THREADS")) T = atoi(e);  // tuning experiments only
+  if (gram && tune.gram_threads > 0) T = tune.gram_threads;
+  if (tune.threads > 0) T = tune.threads;  // tuning experiments only
   if (T != 128 && T != 256 && T != 512 && T != 1024) return cudaErrorInvalidValue;
   // Gram kernel shared-memory plan: fixed state, then (staged) W / WR, then the packed Gram block
   // of the warp sweep in whatever is left of the CTA's share of the SM (two CTAs per SM up to 256
   // threads, one above).
   const size_t smem_g0 = kFixedSmem + kGramSmem, smem_gw = (size_t)2 * ldx * 8;
   int ctas = T <= 128 ? 4 : T <= 256 ? 2 : 1;  // resident CTAs per SM the register cap allows
-  if (const char* e = getenv("SAVER_GRAM_CTAS")) { const int c = atoi(e); if (c >= 1 && c < ctas) ctas = c; }
+  if (tune.gram_ctas >= 1 && tune.gram_ctas < ctas) ctas = tune.gram_ctas;
   size_t budget = (size_t)(228 * 1024 - ctas * 1024) / ctas / 16 * 16;
   if (budget > 227 * 1024) budget = 227 * 1024;
   bool gram_staged = smem_g0 + smem_gw <= budget;
-  if (const char* e = getenv("SAVER_GRAM_STAGED")) gram_staged = gram_staged && atoi(e) != 0;
+  if (tune.gram_staged >= 0) gram_staged = gram_staged && tune.gram_staged != 0;
   if (!gram_staged && smem_g0 > budget) budget = 227 * 1024;
   size_t smem_gram = smem_g0 + (gram_staged ? smem_gw : 0);
   {
     size_t hs = smem_gram < budget ? (budget - smem_gram) / 16 * 16 : 0;
-    if (const char* e = getenv("SAVER_GRAM_HS")) { const size_t cap = (size_t)atol(e); if (hs > cap) hs = cap / 16 * 16; }
+    if (tune.gram_hs >= 0 && hs > (size_t)tune.gram_hs) hs = (size_t)tune.gram_hs / 16 * 16;
     int mh = 0;
     while (mh < 256 && (size_t)(mh + 1) * (mh + 2) / 2 * 8 <= hs) ++mh;
     A.mh = mh;
@@ -2612,7 +2550,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
     bool want = true;
-    if (const char* e = getenv("SAVER_L2_PERSIST")) want = atoi(e) != 0;
+    if (tune.l2_persist >= 0) want = tune.l2_persist != 0;
     if (want && max_persist > 0 && max_window > 0) {
       size_t bytes = (size_t)ldx * D.p * sizeof(double);
       if (bytes > (size_t)max_window) bytes = (size_t)max_window;
@@ -2640,6 +2578,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     int* cnt = ws.counters + (cur ? 0 : 1);
     if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
     cudaEventRecord(ws.ev[0], s);
+    A.round_no = rounds;
     if (gram) {
       const size_t sm = smem_gram;
       switch (T) {
@@ -2659,7 +2598,18 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     *launches += 1;
     cudaEventRecord(ws.ev[1], s);
     if ((e = cudaMemcpyAsync(ws.h_counter, cnt, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) {
+      if (ws.h_crumb) {  // the mapped breadcrumbs survive the fault: CTAs that never reached tag 10
+        fprintf(stderr, "lasso_run: round %d (live %d, T %d) failed: %s\n", rounds, live, T, cudaGetErrorString(e));
+        for (int c = 0; c < kCrumbSlots; ++c) {
+          const int* r = ws.h_crumb + (size_t)c * 8;
+          if (r[2] != 0 && r[2] != 10)
+            fprintf(stderr, "  crumb slot %d: round %d pid %d tag %d lidx %d nin %d nS %d m %d ninact %d\n",
+                    c, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+        }
+      }
+      return e;
+    }
     {
       float ms = 0;
       cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]);

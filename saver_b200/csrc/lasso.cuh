@@ -7,6 +7,7 @@ namespace saver {
 constexpr int kNX = 640;     // capacity of the ever-active list (glmnet pmax = min(2*dfmax+20, nvars))
 constexpr int kNLam = 128;   // capacity of a lambda sequence (glmnet nlambda = 100)
 constexpr int kMaxFolds = 16;
+constexpr int kCrumbSlots = 16384;
 
 enum ProbState : int { ST_INIT = 0, ST_SOLVE = 1, ST_WAIT_KKT = 2, ST_DONE = 3 };
 
@@ -23,7 +24,6 @@ struct LassoProb {
   int ngrad;    // full-gradient (X^T r over all p) rounds so far
   int mtrain;   // training rows
   int slot;     // column of R / G this problem used in the last round
-  int resumed;  // the last launch gave up its time slice mid-solve: force one more IRLS step
   double al, al0;   // current / previous lambda
   double az;        // intercept
   double qv;        // observation weight 1 / mtrain
@@ -48,15 +48,34 @@ struct LassoParams {
   double alf_tall;  // lambda ratio for flmin = 1e-4
   int gram = 1;     // 1: Gram-space round kernel (default), 0: n-space kernel that mirrors fishnet1's iterate sequence
   double strong_slack = 1.0;  // screening margin below lambda in units of the lambda step (1 = strong rule)
-  long long slice_cycles = 0;  // time slice of a round-kernel CTA in SM cycles (0: none), set by lasso_run
   int dbg = 0;      // bisection switches for bring-up (SAVER_LASSO_DBG), 0 in production
+};
+
+// Developer overrides of the solver's launch plan.  Read from the environment ONCE, when the handle
+// is created (saver_cuda_create); nothing on the per-block path calls getenv.
+struct LassoTuning {
+  int problems = 0;        // SAVER_LASSO_PROBLEMS: problems in flight per block (0 = default)
+  int dbg = -1;            // SAVER_LASSO_DBG: bring-up bits (-1 = use the handle option)
+  int gram = -1;           // SAVER_LASSO_GRAM: force the round kernel variant
+  int threads = 0;         // SAVER_LASSO_THREADS / SAVER_GRAM_THREADS: CTA size
+  int gram_threads = 0;
+  int gram_ctas = 0;       // SAVER_GRAM_CTAS: resident CTAs per SM to plan shared memory for
+  int gram_staged = -1;    // SAVER_GRAM_STAGED: 0 = working weights / residual stay in global memory
+  long gram_hs = -1;       // SAVER_GRAM_HS: cap (bytes) of the packed Gram block in shared memory
+  int l2_persist = -1;     // SAVER_L2_PERSIST: 0 = no persisting-L2 window on the design
+  double strong_slack = -1.0;  // SAVER_STRONG_SLACK
+  void from_env();
 };
 
 // Device workspace of one block of problems (owned by the handle, grown on demand).
 struct LassoWs {
+  LassoTuning tune;
   size_t cap_bytes = 0;
   unsigned char* base = nullptr;
   int *h_counter = nullptr;  // pinned host mirror of the active-problem counter
+  // fault breadcrumbs (lasso_dbg bit 4096): mapped pinned host memory that survives a device fault;
+  // kCrumbSlots records of 8 ints, one per resident CTA slot, rewritten at every phase boundary
+  int *h_crumb = nullptr, *d_crumb = nullptr;
   // carved pointers (valid for the current block)
   double *R, *W, *WR;        // ldx x P_pad panels: GEMM operand, working weights, working residual
   double *G, *XM, *XI;       // p_pad x P_pad tables: gradient, per-fit mean and 1/sd of Xs columns

@@ -39,6 +39,7 @@ int saver_cuda_create(int device, saver_cuda_handle* out) {
   saver_cuda_ctx* h = new (std::nothrow) saver_cuda_ctx();
   if (!h) return SAVER_ERR_NOMEM;
   h->device = device;
+  h->lasso.tune.from_env();  // developer overrides are read once, here
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
@@ -270,8 +271,9 @@ int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int
   if (!h) return SAVER_ERR_ARG;
   if (!h->design.Xs) return fail(h, SAVER_ERR_STATE, "predict_cv: call saver_cuda_set_design first");
   if (!Y || !foldid || !mu || !fit4 || !status || B < 0 || nfolds < 3 || nfolds > kMaxFolds ||
-      nlambda < 1 || nlambda > kNLam || dfmax < 1 || !(thresh > 0))
-    return fail(h, SAVER_ERR_ARG, "predict_cv: bad arguments");
+      nlambda < 1 || nlambda > kNLam || dfmax < 1 || 2 * (long long)dfmax + 20 > kNX || !(thresh > 0))
+    return fail(h, SAVER_ERR_ARG, "predict_cv: bad arguments (3 <= nfolds <= %d, 1 <= nlambda <= %d, 1 <= dfmax <= %d, thresh > 0)",
+                kMaxFolds, kNLam, (kNX - 20) / 2);
   if (B == 0) return SAVER_OK;
   CU(cudaSetDevice(h->device));
   const bool dev = device_ptrs != 0;
@@ -296,7 +298,7 @@ int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int
   prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg;
   prm.alf_wide = lambda_ratio(0.01, nlambda);
   prm.alf_tall = lambda_ratio(1e-4, nlambda);
-  const int chunk = lasso_max_block(prm.NF, D);
+  const int chunk = lasso_max_block(prm.NF, D, h->lasso.tune);
   for (int b0 = 0; b0 < B; b0 += chunk) {
     prm.B = B - b0 < chunk ? B - b0 : chunk;
     CU(lasso_run(D, h->lasso, prm, dY.d + n * b0, dFold.d + n * b0, dSelf.d ? dSelf.d + b0 : nullptr,
@@ -315,8 +317,8 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
                             int* status, int* stats, int device_ptrs) {
   if (!h) return SAVER_ERR_ARG;
   if (!h->design.Xs) return fail(h, SAVER_ERR_STATE, "predict_path: call saver_cuda_set_design first");
-  if (!Y || !mu || !status || !lambda_max || !lambda_min || B < 0 || dfmax < 1 || !(thresh > 0))
-    return fail(h, SAVER_ERR_ARG, "predict_path: bad arguments");
+  if (!Y || !mu || !status || !lambda_max || !lambda_min || B < 0 || dfmax < 1 || 2 * (long long)dfmax + 20 > kNX || !(thresh > 0))
+    return fail(h, SAVER_ERR_ARG, "predict_path: bad arguments (1 <= dfmax <= %d, thresh > 0)", (kNX - 20) / 2);
   if (B == 0) return SAVER_OK;
   CU(cudaSetDevice(h->device));
   const bool dev = device_ptrs != 0;
@@ -366,7 +368,7 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
   prm.NF = 1; prm.nfolds = 0; prm.auto_lambda = 0; prm.dfmax = dfmax; prm.nlam = 0;
   prm.thr = thresh; prm.maxit = 100000;
   prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.alf_wide = prm.alf_tall = 1.0;
-  const int chunk = lasso_max_block(prm.NF, D);
+  const int chunk = lasso_max_block(prm.NF, D, h->lasso.tune);
   DevBuf<int> fold;
   DevBuf<double> fit4;
   CU(fold.alloc(n * (size_t)(B < chunk ? B : chunk), s));

@@ -58,7 +58,7 @@ cudaError_t launch_colmax(const double* C, int ldc, int p, int B, const int* sel
                           cudaStream_t s);
 
 // Batched Poisson-lasso paths of one block of genes (lasso.cu).  Device pointers throughout.
-int lasso_max_block(int NF, const DesignState& D);
+int lasso_max_block(int NF, const DesignState& D, const LassoTuning& tune);
 cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm, const double* Yn,
                       const int* fold, const int* self, const double* lam_user,
                       const int* nlam_user, const double* lmin_user, double* MU, double* out4,

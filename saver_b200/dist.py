@@ -28,6 +28,8 @@ class Comm:
         self.backend = dist.get_backend()
         self.device = (torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
                        if self.backend == "nccl" else torch.device("cpu"))
+        self.bytes_broadcast = 0   # payload bytes this rank sent / received in broadcasts (NVLink)
+        self.bytes_gathered = 0    # payload bytes of all_gather results
 
     def _t(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
@@ -49,12 +51,23 @@ class Comm:
         outs = [self.torch.empty((k, mx), dtype=self.torch.float64, device=self.device)
                 for _ in range(self.world)]
         self.dist.all_gather(outs, self._t(pad))
+        self.bytes_gathered += k * mx * 8 * self.world
         return [o.cpu().numpy()[:, :int(sizes[r])] for r, o in enumerate(outs)]
 
+    def bcast_obj(self, obj, src=0):
+        """Small picklable object (the plan of a root-only saver() call) from src to every rank."""
+        box = [obj if self.rank == src else None]
+        self.dist.broadcast_object_list(box, src=src, device=self.device)
+        return box[0]
+
     def broadcast_array(self, arr, shape=None, src=0, keep_on_device=False):
-        """Broadcast a float64 array from src; other ranks pass arr=None and the shape."""
+        """Broadcast a float64 array from src; other ranks pass arr=None.  A CUDA tensor on src is
+        sent as it is (no host round trip)."""
         if self.rank == src:
-            t = self._t(np.asarray(arr, dtype=np.float64))
+            if isinstance(arr, np.ndarray) or not hasattr(arr, "is_cuda"):
+                t = self._t(np.asarray(arr, dtype=np.float64))
+            else:
+                t = arr.to(self.device).contiguous()
             shp = self.torch.tensor(list(t.shape) + [0] * (4 - t.dim()), dtype=self.torch.int64,
                                     device=self.device)
         else:
@@ -64,6 +77,7 @@ class Comm:
         if self.rank != src:
             t = self.torch.empty(dims, dtype=self.torch.float64, device=self.device)
         self.dist.broadcast(t, src)
+        self.bytes_broadcast += t.numel() * t.element_size()
         return t if keep_on_device else t.cpu().numpy()
 
     def max_scalar(self, v):

@@ -391,7 +391,7 @@ class _Fit:
 
 def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, null_model,
               ngenes=None, ncells=None, gene_names=None, cell_names=None, estimates_only=False,
-              *, self_col=None, backend=None, comm=None, perm="identity", fold_seed=0,
+              *, self_col=None, backend=None, comm=None, perm=None, fold_seed=0,
               fold_method="philox", nfolds=5, keep_mu=False, messages=None, gather=True,
               counts=None):
     """saver.fit (R/saver_fit.R:56-463): the stage schedule.
@@ -399,9 +399,13 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
     x (genes x cells counts), x_est ((p, n) = t(x.est) of R/saver.R:157, gene-major),
     pred_genes / pred_cells 0-based.  self_col[g]: the x_est column carrying gene g's own name or
     -1 (R/calc_estimate.R:103 compares names; indices here).
-    perm: "identity", an int seed or ("R", seed) (gene_order) -- the reference permutes genes with the ambient RNG
-    (R/saver_fit.R:87-92); the permutation only decides which genes get cross-validated in
-    do.fast and the per-gene seeds."""
+    perm: the reference always permutes the genes with the ambient RNG (R/saver_fit.R:87-92); the
+    order decides which genes feed the two schedule regressions of do.fast and the per-gene seeds.
+    None (default) = a random permutation seeded with fold_seed; an int = that seed; ("R", seed) =
+    the order R itself draws after set.seed(seed); "identity" = matrix order, an explicit opt-in for
+    tests and benchmarks only (real matrices are often sorted, which would bias the schedule)."""
+    if perm is None:
+        perm = int(fold_seed)
     msg = messages or (lambda *a: None)
     ngenes = x.shape[0] if ngenes is None else ngenes
     ncells = x.shape[1] if ncells is None else ncells
@@ -418,13 +422,14 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
     pred1 = pred_genes[rs > 0]
     npred = pred_genes.size
     if not null_model:
-        msg("Calculating predictions for %d genes using %d genes and %d cells..."
-            % (npred, x_est.shape[0], x_est.shape[1]))
-        if comm is not None and comm.world > 1 and comm.backend == "nccl" \
-                and isinstance(x_est, np.ndarray):
-            # the design is uploaded once by rank 0 and broadcast over NVLink (NCCL)
+        if x_est is not None:
+            msg("Calculating predictions for %d genes using %d genes and %d cells..."
+                % (npred, x_est.shape[0], x_est.shape[1]))
+        if comm is not None and comm.world > 1 and (x_est is None or comm.backend == "nccl"):
+            # the design is uploaded once by rank 0 and broadcast (NCCL over NVLink on a GPU box);
+            # the other ranks never derive it (x_est is None there in a root-only call)
             backend.set_design(comm.broadcast_array(x_est if comm.rank == 0 else None,
-                                                    keep_on_device=True))
+                                                    keep_on_device=comm.backend == "nccl"))
         else:
             backend.set_design(x_est)
     else:
@@ -455,7 +460,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
             fit.gather()
         info["total.time"] = time.time() - st
         return dict(estimate=fit.est, se=fit.se, info=info, mu=fit.mu, status=fit.status,
-                    seed_of=fit.seed_of)
+                    seed_of=fit.seed_of, owner=fit.owner)
 
     if npred == 0:
         return finish(0)
@@ -562,17 +567,52 @@ def saver_fit_null(x, ncores, sf, scale_sf, estimates_only=False, backend=None, 
 def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=None,
           pred_genes=None, pred_genes_only=False, null_model=False, mu=None,
           estimates_only=False, *, gene_names=None, cell_names=None, backend=None, comm=None,
-          perm="identity", fold_seed=0, fold_method="philox", nfolds=5, return_mu=False,
-          verbose=False):
+          perm=None, fold_seed=0, fold_method="philox", nfolds=5, return_mu=False,
+          verbose=False, gather=True):
     """saver() (R/saver.R:98-179).  x: genes x cells counts (numpy array or scipy.sparse).
 
     pred_cells / pred_genes are 0-based.  ``ncores`` is accepted for signature compatibility;
     device parallelism (one process per GPU, ``comm``) replaces the PSOCK workers.  Returns a
-    SaverResult (or the estimate matrix when ``estimates_only``), exactly as the reference."""
+    SaverResult (or the estimate matrix when ``estimates_only``), exactly as the reference.
+
+    Multi-GPU (``comm``): every stage's genes are dealt over the ranks.  Either every rank passes
+    the same x, or only rank 0 does and the others pass ``x=None`` (root-only: rank 0 prepares the
+    design, one broadcast ships it).  ``gather=False`` leaves each rank with the rows it computed
+    (``result.owner`` tells which) instead of all-gathering estimate / se to every rank -- the
+    sink is host memory, so no collective is needed for the results."""
     msg = (lambda s: print(s, flush=True)) if verbose else (lambda s: None)
-    if mu is not None:
-        mu = check_mu(x, mu)
-    x, kept = clean_data(x)
+    world = comm.world if comm is not None else 1
+    # Root-only call (one process per GPU, only rank 0 holds the matrix -- the reference's own
+    # parallel contract: one x, chunks exported to the workers, R/calc_estimate.R:69-74): rank 0
+    # does the host preparation once, the design goes out with one broadcast, the others receive
+    # the plan and the counts of the genes to process.  x = None on a rank selects it.
+    root_only = world > 1 and comm.max_scalar(1.0 if x is None else 0.0) > 0
+    if root_only and comm.rank != 0:
+        plan = comm.bcast_obj(None)
+        if plan.get("error"):
+            raise SaverError(plan["error"])
+        x = comm.broadcast_array(None)
+        backend = backend or CudaBackend(comm=comm)
+        out = saver_fit(x, None, do_fast, ncores, plan["sf"], plan["scale_sf"], plan["pg"],
+                        plan["pc"], null_model, estimates_only=estimates_only,
+                        self_col=plan["self_col"], backend=backend, comm=comm, perm=perm,
+                        fold_seed=fold_seed, fold_method=fold_method, nfolds=nfolds,
+                        keep_mu=return_mu, messages=msg, gather=gather)
+        gene_names, cell_names = plan["gene_names"], plan["cell_names"]
+        sf, scale_sf = plan["sf"], plan["scale_sf"]
+        return _saver_result(out, x, sf, scale_sf, gene_names, cell_names, estimates_only,
+                             return_mu, gather)
+    try:
+        if root_only and (mu is not None or hasattr(x, "tocsc")):
+            raise SaverError("a root-only saver() call (x = None on the other ranks) takes a dense "
+                             "matrix and no mu; pass x on every rank instead")
+        if mu is not None:
+            mu = check_mu(x, mu)
+        x, kept = clean_data(x)
+    except SaverError as e:
+        if root_only:
+            comm.bcast_obj({"error": str(e)})
+        raise
     if cell_names is not None:
         cell_names = np.asarray(cell_names)[kept]
     ngenes, ncells = x.shape
@@ -585,7 +625,7 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
     sf, scale_sf = calc_size_factor(x if dc is None else _Sums(dc), size_factor, ncells)
     if mu is not None:
         out = saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only, backend, comm, dc)
-    elif null_model:
+    elif null_model and not root_only:
         out = saver_fit_null(x, ncores, sf, scale_sf, estimates_only, backend, comm, dc)
     else:
         pc = get_pred_cells(pred_cells, ncells)
@@ -593,7 +633,9 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
         rm = np.asarray(x.mean(1)).ravel() if dc is None else dc.row_sums / ncells
         good = np.where(rm >= 0.1)[0]
         # x.est = t(log((x[good, ] + 1) / sf))  (R/saver.R:156-157), kept gene-major: (p, n)
-        if dc is not None:
+        if null_model:
+            x_est = None
+        elif dc is not None:
             x_est = dc.log_rows(good, sf)
         else:
             x_est = np.log((_dense_rows(x, good) + 1.0) / sf)
@@ -609,17 +651,27 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
             gene_names = np.asarray(gene_names)[pg]
             self_col = self_col[pg]
             pg = np.arange(x.shape[0])
+        if root_only:
+            comm.bcast_obj(dict(sf=sf, scale_sf=scale_sf, pg=pg, pc=pc, self_col=self_col,
+                                gene_names=gene_names, cell_names=cell_names))
+            comm.broadcast_array(x)   # counts of the genes to process (the whole x, or x[pred.genes, ])
         out = saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pg, pc, null_model,
                         estimates_only=estimates_only, self_col=self_col, backend=backend,
                         comm=comm, perm=perm, fold_seed=fold_seed, fold_method=fold_method,
-                        nfolds=nfolds, keep_mu=return_mu, messages=msg, counts=dc)
+                        nfolds=nfolds, keep_mu=return_mu, messages=msg, counts=dc, gather=gather)
     msg("Done!")
+    return _saver_result(out, x, sf, scale_sf, gene_names, cell_names, estimates_only, return_mu,
+                         gather)
+
+
+def _saver_result(out, x, sf, scale_sf, gene_names, cell_names, estimates_only, return_mu, gather):
     res = SaverResult(out["estimate"], out["se"], out["info"], out.get("mu"), gene_names,
                       cell_names)
     res.status = out.get("status")
     res.seed_of = out.get("seed_of")
-    res.x, res.sf, res.scale_sf = x, sf, scale_sf
-    if estimates_only and not return_mu:
+    res.owner = out.get("owner")   # rank that computed each row (rows of other ranks are only
+    res.x, res.sf, res.scale_sf = x, sf, scale_sf   # filled in when gather=True)
+    if estimates_only and not return_mu and gather:
         return res.estimate
     return res
 

@@ -41,6 +41,8 @@ SEXP Rf_allocMatrix(unsigned int type, int nrow, int ncol);
 int Rf_nrows(SEXP x);
 int Rf_ncols(SEXP x);
 Rboolean Rf_isNull(SEXP x);
+Rboolean Rf_isReal(SEXP x);
+Rboolean Rf_isInteger(SEXP x);
 int Rf_asInteger(SEXP x);
 double Rf_asReal(SEXP x);
 int Rf_asLogical(SEXP x);

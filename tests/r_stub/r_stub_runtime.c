@@ -89,6 +89,8 @@ API int Rf_length(SEXP x) { return (int)x->len; }
 API int Rf_nrows(SEXP x) { if (x->nrow < 0) Rf_error("object is not a matrix"); return x->nrow; }
 API int Rf_ncols(SEXP x) { if (x->ncol < 0) Rf_error("object is not a matrix"); return x->ncol; }
 API Rboolean Rf_isNull(SEXP x) { return x->type == NILSXP ? TRUE : FALSE; }
+API Rboolean Rf_isReal(SEXP x) { return x->type == REALSXP ? TRUE : FALSE; }
+API Rboolean Rf_isInteger(SEXP x) { return x->type == INTSXP ? TRUE : FALSE; }
 API double Rf_asReal(SEXP x)
 {
     if (x->len < 1) Rf_error("stub runtime: asReal of an empty value");

@@ -87,7 +87,7 @@ def test_saver_slow_schedule_equals_direct_oracle_calls():
     x = _small()[:40]
     be = OracleBackend()
     import saver_b200
-    res = saver_b200.saver(x, do_fast=False, backend=be, fold_seed=3, return_mu=True)
+    res = saver_b200.saver(x, do_fast=False, backend=be, fold_seed=3, return_mu=True, perm="identity")
     # slow schedule = stages of n1 = 8, ceil((npred-8)/4), rest, all cross-validated; then the rest
     npred = int((res.x.sum(1) > 0).sum())
     stages = [c for c in be.calls]
