@@ -51,6 +51,7 @@ WORKLOADS = {
     "tiny": dict(G=256, n=300, seed=20299, block=0),
     "null": dict(G=20000, n=10000, seed=20263, block=0),
     "fast": dict(G=5000, n=2000, seed=20262, block=0),
+    "cfg5": dict(G=20000, n=10000, seed=20265, block=0),
 }
 METRIC = "genes/sec, full saver() (cv Poisson lasso + variance fit + posterior), synthetic NB"
 
@@ -149,14 +150,11 @@ def stage_layout(B):
 
 def deal(B, rank, world):
     """Block positions this rank computes and their cv seeds j -- exactly what saver() does with the
-    block: every stage is dealt round-robin over the ranks, j = 1-based position inside the stage
+    block: genes dealt round-robin over the ranks, j = 1-based position inside the gene's stage
     (R/calc_estimate.R:98), so the resident arm, the e2e arm and the oracle see the same folds."""
-    pos, seeds = [], []
-    for a, b in stage_layout(B):
-        q = np.arange(a, b)[rank::world]
-        pos.append(q)
-        seeds.append(q - a + 1)
-    return np.concatenate(pos), np.concatenate(seeds)
+    seed_of = np.concatenate([np.arange(1, b - a + 1) for a, b in stage_layout(B)])
+    pos = np.arange(B)[rank::world]
+    return pos, seed_of[pos]
 
 
 def counters(h):
@@ -500,24 +498,44 @@ def run_reference(args):
     nsteps = args.warmup + args.steps
     times, done = [], []
     last = 0.0
+    mine, seeds = deal(B, 0, 1)
     if inside:
-        # one gene per step would be minutes: a step = the genes that fit ~10 s on this box, with the
-        # threads working INSIDE a gene (5 fold fits at a time x column threads)
-        per_step = max(1, args.ref_genes)
-        sample = "%d gene(s) of the block per step, threads inside the gene (%d fold fits x %d column threads)" % (
-            per_step, outer, inner)
+        # A gene is minutes of scalar work at this shape, so a step is ONE glmnet fit of the gene's
+        # six (the master fit, then the five fold fits on the master's lambda list), with every host
+        # thread working inside the fit (column loops of the KKT / curvature passes); 6 steps = 1 gene.
+        oracle.set_threads(1, cores)
+        sample = ("one glmnet fit per step (master fit, then the 5 fold fits on its lambda list; 6 steps "
+                  "= 1 gene), %d threads inside the fit" % cores)
+        state = {}
+        for it in range(nsteps):
+            gi, f = divmod(it, 6)
+            pos = (gi * max(1, B // (nsteps // 6 + 1))) % B
+            g = genes[pos]
+            y = xc[g] / sf
+            t0 = time.time()
+            if f == 0 or "lam" not in state:
+                r = oracle.glmnet_poisson(x_est, y, excl=int(self_col[g]))
+                state = {"lam": r["lam"], "fold": host.draw_folds([seeds[pos]], n, 5, args.fold_seed)[0]}
+            else:
+                rows = np.where(state["fold"] != f)[0]
+                r = oracle.glmnet_poisson(x_est, y, rows=rows, excl=int(self_col[g]), lam=state["lam"])
+            dt = time.time() - t0
+            if it >= args.warmup:
+                times.append(dt)
+                done.append(1.0 / 6.0)
+            last = dt
+        oracle.set_threads(1, 1)
     else:
         per_step = 2 * cores
         sample = "%d genes of the block per step, one gene per thread (dynamic)" % per_step
-    for it in range(nsteps):
-        sel = (np.arange(per_step) * max(1, B // (per_step * nsteps)) + it * per_step) % B
-        mine, seeds = deal(B, 0, 1)
-        dt, _ = oracle_sample(x_est, xc, sf, scale_sf, self_col, genes[sel], seeds[np.searchsorted(mine, sel)],
-                              args.fold_seed, inside)
-        if it >= args.warmup:
-            times.append(dt)
-            done.append(sel.size)
-        last = dt
+        for it in range(nsteps):
+            sel = (np.arange(per_step) * max(1, B // (per_step * nsteps)) + it * per_step) % B
+            dt, _ = oracle_sample(x_est, xc, sf, scale_sf, self_col, genes[sel], seeds[sel],
+                                  args.fold_seed, inside)
+            if it >= args.warmup:
+                times.append(dt)
+                done.append(sel.size)
+            last = dt
     tot = float(np.sum(times))
     value = float(np.sum(done)) / tot
     line = {
@@ -547,13 +565,12 @@ def main():
                     help="draw another block of genes over the same cells (synth.nb_counts)")
     ap.add_argument("--fold-seed", type=int, default=5)
     ap.add_argument("--parity", type=int, default=None, help="genes checked against the CPU oracle")
-    ap.add_argument("--ref-genes", type=int, default=1, help="genes per step of the reference arm (large n)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) arm")
     ap.add_argument("--e2e-steps", type=int, default=1)
     args = ap.parse_args()
     try:
-        if args.workload in ("null", "fast") and args.impl == "cuda":
+        if args.workload in ("null", "fast", "cfg5") and args.impl == "cuda":
             import bench_extra
             bench_extra.run(args)
         elif args.impl == "reference":

@@ -1,0 +1,314 @@
+"""bench_extra.py -- the non-headline workloads of bench.py (same JSON contract, one line, rank 0).
+
+    python bench.py --workload null     saver(x, null.model = TRUE, estimates.only = TRUE), 20k x 10k
+                                         = calc.b + Gamma posterior for every gene (variance.cu alone)
+    python bench.py --workload fast     saver(x, do.fast = TRUE) on 5,000 x 2,000 (the default schedule)
+    python bench.py --workload cfg5     sample.saver (gamma + NB) and cor.genes on 20k x 10k est / se
+
+N > 1: genes (null, sample) or column panels (cor.genes) are dealt in contiguous blocks over the
+ranks, no data-path collective; time = max over ranks.
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+
+def _env():
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libsaver_cuda has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        import torch.distributed as tdist
+        from saver_b200 import dist as sdist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=dev)
+        comm = sdist.Comm(init=False)
+    return torch, rank, world, local, dev, comm
+
+
+def _max_over_ranks(comm, vals, dev, torch):
+    if comm is None:
+        return [float(v) for v in vals]
+    t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=dev)
+    import torch.distributed as tdist
+    tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu().numpy()]
+
+
+def _finish(comm):
+    if comm is not None:
+        import torch.distributed as tdist
+        comm.barrier()
+        tdist.destroy_process_group()
+
+
+def _timed(fn, steps, warmup, stream, flush, torch, barrier):
+    for _ in range(warmup):
+        flush.zero_()
+        fn()
+    barrier()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in evs) / 1e3
+
+
+def run(args):
+    if args.workload == "null":
+        run_null(args)
+    elif args.workload == "fast":
+        run_fast(args)
+    else:
+        run_cfg5(args)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_null(args):
+    import bench
+    import saver_b200
+    from saver_b200 import host, ops
+    torch, rank, world, local, dev, comm = _env()
+    h = saver_b200.Handle(local)
+    stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+    w = bench.WORKLOADS["null"]
+    G, n = (w["G"], w["n"]) if args.block is None else (args.block, w["n"])
+    from saver_b200 import synth
+    x = synth.nb_counts(G, n, w["seed"])          # every rank draws the same matrix, keeps its block
+    xc, _ = host.clean_data(x)
+    sf, scale_sf = host.calc_size_factor(xc, None, n)
+    e = [(G * r) // world for r in range(world + 1)]
+    mine = np.arange(e[rank], e[rank + 1])
+    Xd = torch.from_numpy(np.ascontiguousarray(xc[mine])).to(dev)
+    sfd = torch.from_numpy(sf).to(dev)
+    mud = (Xd / sfd).mean(1).contiguous()           # null model: mu = mean(y / sf) per gene
+    est = torch.empty_like(Xd)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    blk = 4096
+
+    def barrier():
+        h.synchronize()
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
+
+    def step():
+        for b0 in range(0, mine.size, blk):
+            sl = slice(b0, min(b0 + blk, mine.size))
+            ops.calc_post(Xd[sl], mud[sl], sfd, scale_sf, want_se=False, want_info=False,
+                          out={"est": est[sl]}, handle=h)
+
+    clocks = bench.ClockSampler(local)
+    l0 = h.launch_count()
+    clocks.start()
+    t = _timed(step, args.steps, args.warmup, stream, flush, torch, barrier)
+    clk = clocks.stop()
+    launches = h.launch_count() - l0
+    # e2e through the public API from host buffers
+    be = host.CudaBackend(handle=h)
+    sub = xc[mine]
+    saver_b200.saver(sub[:64], null_model=True, estimates_only=True, backend=be)
+    barrier()
+    t0 = time.time()
+    est_h = saver_b200.saver(sub, null_model=True, estimates_only=True, backend=be)
+    h.synchronize()
+    e2e = time.time() - t0
+    tmax, e2e_max = _max_over_ranks(comm, [t, e2e], dev, torch)
+    parity = None
+    if rank == 0:
+        import oracle
+        k = min(16, mine.size)
+        sel = np.linspace(0, mine.size - 1, k).astype(int)
+        t0 = time.time()
+        ref = oracle.calc_post_batch(sub[sel], np.repeat((sub[sel] / sf).mean(1)[:, None], n, 1), sf, scale_sf)
+        dt = time.time() - t0
+        got = est[torch.from_numpy(sel).to(dev)].cpu().numpy()
+        rel = np.abs(got - ref["est"]) / np.maximum(ref["est"], 1e-12)
+        parity = {"genes": int(k), "max_rel_err_estimate": float(rel.max()),
+                  "quantum": "values are ceiling(v * 1000) / 1000: one quantum = 1e-3 absolute",
+                  "max_abs_err": float(np.abs(got - ref["est"]).max()),
+                  "e2e_equal_resident": bool(np.array_equal(est_h[sel], got))}
+        cpu = {"value": k / dt * (os.cpu_count() or 1) / min(k, os.cpu_count() or 1), "unit": "genes/s",
+               "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "%d genes, one gene per thread, %.2f s" % (k, dt)}
+        hbm, which = bench.peaks()
+        bytes_step = 16.0 * n * G    # read y + write est (scalar mu, estimates.only); sf amortised
+        line = {
+            "metric": "genes/sec, saver(null.model = TRUE, estimates.only = TRUE), synthetic NB",
+            "value": G * args.steps / tmax, "unit": "genes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tmax * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "null: %d genes x %d cells, calc.b (Brent + grid branch) + Gamma posterior "
+                                   "for every gene" % (G, n), "l2": "flushed between steps (256 MiB write)"},
+            "clocks": clk,
+            "e2e": {"value": G / e2e_max, "unit": "genes/s", "h2d_bytes_per_step": int(sub.nbytes * world),
+                    "d2h_bytes_per_step": int(sub.nbytes * world), "s_per_step": e2e_max,
+                    "api": "saver_b200.saver(x, null_model=True, estimates_only=True)"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "calc_post_kernel", "bound": "hbm", "unit": "GB/s",
+                         "achieved": bytes_step * args.steps / tmax / 1e9, "peak": hbm,
+                         "frac": bytes_step * args.steps / tmax / 1e9 / hbm, "peak_source": which,
+                         "traffic": None,
+                         "algorithmic": "16*n B/gene (read y, write est; scalar mu, estimates.only)",
+                         "note": "the kernel is FP64-transcendental bound (one log per cell and one "
+                                 "log-of-product per non-zero cell per likelihood evaluation); see "
+                                 "profiles/ for the FP64-pipe utilisation"},
+            "parity": parity, "cpu_baseline": cpu if world == 1 else None,
+        }
+        print(json.dumps(line), flush=True)
+    _finish(comm)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_fast(args):
+    import bench
+    import saver_b200
+    from saver_b200 import host
+    torch, rank, world, local, dev, comm = _env()
+    h = saver_b200.Handle(local)
+    w = bench.WORKLOADS["fast"]
+    x = bench.make_counts("fast") if rank == 0 or comm is None else None
+    be = host.CudaBackend(handle=h, comm=comm)
+
+    def barrier():
+        h.synchronize()
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
+
+    kw = dict(do_fast=True, estimates_only=False, fold_seed=args.fold_seed, perm=args.fold_seed,
+              backend=be, comm=comm, gather=False)
+    clocks = bench.ClockSampler(local)
+    times = []
+    l0 = h.launch_count()
+    res = None
+    for it in range(args.warmup + args.steps):
+        barrier()
+        if it == args.warmup:
+            clocks.start()
+            l0 = h.launch_count()
+        t0 = time.time()
+        res = saver_b200.saver(x, **kw)
+        h.synchronize()
+        if it >= args.warmup:
+            times.append(time.time() - t0)
+    clk = clocks.stop()
+    launches = h.launch_count() - l0
+    (tmax,) = _max_over_ranks(comm, [float(np.sum(times))], dev, torch)
+    if rank == 0:
+        info = res.info
+        G = res.x.shape[0]
+        ncv = int((np.isfinite(info["sd.cv"]) & (info["lambda.max"] > 0)).sum())
+        nfix = int(np.isnan(info["sd.cv"]).sum())
+        line = {
+            "metric": "genes/sec, saver(do.fast = TRUE) (default schedule), synthetic NB",
+            "value": G * args.steps / tmax, "unit": "genes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tmax * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fast: %d genes x %d cells, do.fast=TRUE: %d genes cross-validated, %d "
+                                   "fixed-lambda paths, the rest means; estimate + se" % (G, w["n"], ncv, nfix)},
+            "clocks": clk,
+            "e2e": {"value": G * args.steps / tmax, "unit": "genes/s",
+                    "h2d_bytes_per_step": int(res.x.nbytes * 2), "d2h_bytes_per_step": int(res.x.nbytes * 2),
+                    "s_per_step": tmax / args.steps,
+                    "api": "saver_b200.saver(x, do_fast=True): value IS the end-to-end number (the stage "
+                           "schedule needs the host regressions between device passes)"},
+            "gpu_launches": int(launches),
+            "roofline": None,
+        }
+        print(json.dumps(line), flush=True)
+    _finish(comm)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cfg5(args):
+    import bench
+    import saver_b200
+    from saver_b200 import ops
+    torch, rank, world, local, dev, comm = _env()
+    h = saver_b200.Handle(local)
+    stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+    G, n = (20000, 10000) if args.block is None else (args.block, 10000)
+    # est / se of the shape saver() returns at cfg3 (posterior mean / sd of a Gamma): synthetic
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20265)
+    e = [(G * r) // world for r in range(world + 1)]
+    g0, g1 = e[rank], e[rank + 1]
+    est_all = (torch.rand((G, n), generator=gen, device=dev, dtype=torch.float64) * 3.0 + 0.05)
+    se_all = est_all * (0.2 + 0.5 * torch.rand((G, n), generator=gen, device=dev, dtype=torch.float64))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = torch.empty((g1 - g0, n), dtype=torch.float64, device=dev)
+
+    def barrier():
+        h.synchronize()
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
+
+    def samp(nb):
+        def f():
+            blk = 4096
+            for b0 in range(g0, g1, blk):
+                b1 = min(b0 + blk, g1)
+                out[b0 - g0:b1 - g0] = ops.sample(est_all[b0:b1], se_all[b0:b1], nb_mode=nb, seed=50,
+                                                 rep_idx=0, gene0=b0, handle=h)
+        return f
+
+    clocks = bench.ClockSampler(local)
+    l0 = h.launch_count()
+    clocks.start()
+    t_gamma = _timed(samp(False), args.steps, args.warmup, stream, flush, torch, barrier)
+    t_nb = _timed(samp(True), args.steps, args.warmup, stream, flush, torch, barrier)
+    # cor.genes: this rank's column panel of the symmetric G x G matrix
+    del out
+    cor = [None]
+
+    def corf():
+        cor[0] = None
+        cor[0] = ops.cor_adjust(est_all, se_all, by_cells=False, col0=g0, ncols=g1 - g0, handle=h)
+
+    t_cor = _timed(corf, max(1, args.steps // 2), 1, stream, flush, torch, barrier)
+    clk = clocks.stop()
+    launches = h.launch_count() - l0
+    csteps = max(1, args.steps // 2)
+    tg, tn, tc = _max_over_ranks(comm, [t_gamma, t_nb, t_cor], dev, torch)
+    if rank == 0:
+        hbm, which = bench.peaks()
+        d = np.diag(cor[0][:, g0:g1].cpu().numpy()) if g1 - g0 <= 4096 else None
+        sb = 24.0 * n * G
+        line = {
+            "metric": "genes/sec, sample.saver (gamma) on saver() output, 20k x 10k",
+            "value": G * args.steps / tg, "unit": "genes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tg * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5: sample.saver(rep = 1, seed = 50) gamma and NB modes + cor.genes on "
+                                   "est / se of %d genes x %d cells" % (G, n),
+                       "l2": "flushed between steps (256 MiB write)"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": None,
+            "roofline": {"kernel": "sample_kernel (gamma mode)", "bound": "hbm", "unit": "GB/s",
+                         "achieved": sb * args.steps / tg / 1e9, "peak": hbm, "frac": sb * args.steps / tg / 1e9 / hbm,
+                         "peak_source": which, "traffic": None, "algorithmic": "24*n B/gene/rep"},
+            "sample_nb": {"genes_per_s": G * args.steps / tn, "GBps": sb * args.steps / tn / 1e9,
+                          "frac_hbm": sb * args.steps / tn / 1e9 / hbm},
+            "cor_genes": {"s_per_call": tc / csteps, "tflops": 2.0 * G * G * n * csteps / tc / 1e12,
+                          "flops": "2*G^2*n (each rank: a G x G/N column panel, inputs replicated)",
+                          "out_bytes": int(G) * G * 8,
+                          "diag_is_adj2_le_1": None if d is None else bool((d <= 1.0 + 1e-12).all())},
+        }
+        print(json.dumps(line), flush=True)
+    _finish(comm)

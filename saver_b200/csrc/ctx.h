@@ -16,6 +16,7 @@ struct saver_cuda_ctx {
   double ms_post = 0, ms_maxcor = 0;
   int opt_gram = 1;            // saver_cuda_set_option("lasso_gram")
   double opt_strong_slack = 1.0;
+  double opt_inner_scale = 1.0;  // saver_cuda_set_option("inner_scale")
   int opt_dbg = 0;  // device time of the variance/posterior and maxcor phases
   char err[512] = {0};
   saver::DesignState design;

@@ -247,7 +247,7 @@ extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, in
       h->launches += 1;
       LassoParams prm;
       prm.dfmax = dfmax; prm.thr = thresh; prm.maxit = 100000;
-  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg;
+  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.inner_scale = h->opt_inner_scale;
       std::vector<double> lam;
       std::vector<int> nlam;
       std::vector<double> lminp;

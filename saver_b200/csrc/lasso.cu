@@ -1301,6 +1301,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   double al = PR->al, al0 = PR->al0, az = PR->az, v0 = PR->v0, sumr = PR->sumr;
   double cur_dev = PR->cur_dev, cur_cv = PR->cur_cv;
   const double qv = PR->qv, dv0 = PR->dv0, dvr = PR->dvr, shr = PR->shr, ncv = PR->ncv;
+  const double shr_in = shr * A.prm.inner_scale;  // exit test of the Gram-space sweeps
   const int n = A.n, ldx = A.ldx, p = A.p, p_pad = A.p_pad;
   const double* __restrict__ Xs = A.Xs;
   const double* Gc = A.ws.G + (size_t)slot * p_pad;
@@ -2024,7 +2025,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         lap(5);
         if (overflow) break;
         gintercept(m, dlx);
-        if (dlx < shr) break;
+        if (dlx < shr_in) break;
         if (!(dlx == dlx)) { nanfail = true; break; }
         if (nlp > maxit) { maxed = true; break; }
         int inner = 0;
@@ -2033,7 +2034,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
           dlx = 0.0;
           if (!(dbg & 2)) gsweep(false, m, dlx);
           gintercept(m, dlx);
-          if (dlx < shr) break;
+          if (dlx < shr_in) break;
           if (!(dlx == dlx)) { nanfail = true; break; }
           if (nlp > maxit) { maxed = true; break; }
           if (++inner >= 64 && !H_fresh && m > 0) {

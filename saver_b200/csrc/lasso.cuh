@@ -48,6 +48,7 @@ struct LassoParams {
   double alf_tall;  // lambda ratio for flmin = 1e-4
   int gram = 1;     // 1: Gram-space round kernel (default), 0: n-space kernel that mirrors fishnet1's iterate sequence
   double strong_slack = 1.0;  // screening margin below lambda in units of the lambda step (1 = strong rule)
+  double inner_scale = 1.0;   // Gram kernel: the sweeps inside one IRLS step stop at thr * inner_scale * dev0
   int dbg = 0;      // bisection switches for bring-up (SAVER_LASSO_DBG), 0 in production
 };
 

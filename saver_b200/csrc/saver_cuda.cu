@@ -295,7 +295,7 @@ int saver_cuda_predict_cv(saver_cuda_handle h, const double* Y, int B, const int
   LassoParams prm;
   prm.NF = nfolds + 1; prm.nfolds = nfolds; prm.auto_lambda = 1; prm.dfmax = dfmax;
   prm.nlam = nlambda; prm.thr = thresh; prm.maxit = 100000;
-  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg;
+  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.inner_scale = h->opt_inner_scale;
   prm.alf_wide = lambda_ratio(0.01, nlambda);
   prm.alf_tall = lambda_ratio(1e-4, nlambda);
   const int chunk = lasso_max_block(prm.NF, D, h->lasso.tune);
@@ -367,7 +367,7 @@ int saver_cuda_predict_path(saver_cuda_handle h, const double* Y, int B, const i
   LassoParams prm;
   prm.NF = 1; prm.nfolds = 0; prm.auto_lambda = 0; prm.dfmax = dfmax; prm.nlam = 0;
   prm.thr = thresh; prm.maxit = 100000;
-  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.alf_wide = prm.alf_tall = 1.0;
+  prm.gram = h->opt_gram; prm.strong_slack = h->opt_strong_slack; prm.dbg = h->opt_dbg; prm.inner_scale = h->opt_inner_scale; prm.alf_wide = prm.alf_tall = 1.0;
   const int chunk = lasso_max_block(prm.NF, D, h->lasso.tune);
   DevBuf<int> fold;
   DevBuf<double> fit4;
@@ -395,6 +395,10 @@ int saver_cuda_set_option(saver_cuda_handle h, const char* key, double value) {
   if (!strcmp(key, "lasso_gram")) h->opt_gram = value != 0;
   else if (!strcmp(key, "strong_slack")) h->opt_strong_slack = value;
   else if (!strcmp(key, "lasso_dbg")) h->opt_dbg = (int)value;
+  else if (!strcmp(key, "inner_scale")) {
+    if (!(value > 0 && value <= 1)) return fail(h, SAVER_ERR_ARG, "set_option: inner_scale must be in (0, 1]");
+    h->opt_inner_scale = value;
+  }
   else return fail(h, SAVER_ERR_ARG, "set_option: unknown key %s", key);
   return SAVER_OK;
 }

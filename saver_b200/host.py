@@ -331,9 +331,11 @@ class _Fit:
                 self.mu = self.comm.gather_rows(self.mu, self.owner)
 
     def run(self, ind, mode, cutoff, coefs, calc_maxcor, self_col_of, is_pred_of, pred_mask,
-            npred_cells, nfolds, fold_seed, fold_method):
-        """calc.estimate(x[ind, ], ...) for one stage; genes are dealt over the ranks."""
+            npred_cells, nfolds, fold_seed, fold_method, seeds=None):
+        """calc.estimate(x[ind, ], ...) for one stage; genes are dealt over the ranks.  seeds: the
+        cv seed j of every gene of ind (default: its 1-based position, R/calc_estimate.R:98)."""
         ind = np.asarray(ind, dtype=np.int64)
+        seeds = np.arange(1, ind.size + 1) if seeds is None else np.asarray(seeds, dtype=np.int64)
         if ind.size == 0:
             return
         rank, world = (self.comm.rank, self.comm.world) if self.comm else (0, 1)
@@ -353,8 +355,8 @@ class _Fit:
                 # seed j = 1-based position of the gene inside the stage block (R/calc_estimate.R:98)
                 fold = np.zeros((g.size, xb.shape[1]), dtype=np.int32)
                 pc = np.where(pred_mask)[0] if pred_mask is not None else np.arange(xb.shape[1])
-                fold[:, pc] = draw_folds(p + 1, npred_cells, nfolds, fold_seed, fold_method)
-                self.seed_of[g] = p + 1
+                fold[:, pc] = draw_folds(seeds[p], npred_cells, nfolds, fold_seed, fold_method)
+                self.seed_of[g] = seeds[p]
             r = self.backend.calc_estimate(
                 xb, self.sf, self.scale_sf, mode, cutoff=cutoff, coefs=coefs,
                 self_col=self_col_of[g], is_pred=is_pred_of[g], pred_mask=pred_mask, foldid=fold,
@@ -393,7 +395,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
               ngenes=None, ncells=None, gene_names=None, cell_names=None, estimates_only=False,
               *, self_col=None, backend=None, comm=None, perm=None, fold_seed=0,
               fold_method="philox", nfolds=5, keep_mu=False, messages=None, gather=True,
-              counts=None):
+              counts=None, root_design=False):
     """saver.fit (R/saver_fit.R:56-463): the stage schedule.
 
     x (genes x cells counts), x_est ((p, n) = t(x.est) of R/saver.R:157, gene-major),
@@ -425,7 +427,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
         if x_est is not None:
             msg("Calculating predictions for %d genes using %d genes and %d cells..."
                 % (npred, x_est.shape[0], x_est.shape[1]))
-        if comm is not None and comm.world > 1 and (x_est is None or comm.backend == "nccl"):
+        if comm is not None and comm.world > 1 and (root_design or comm.backend == "nccl"):
             # the design is uploaded once by rank 0 and broadcast (NCCL over NVLink on a GPU box);
             # the other ranks never derive it (x_est is None there in a root-only call)
             backend.set_design(comm.broadcast_array(x_est if comm.rank == 0 else None,
@@ -498,19 +500,17 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
         fit.run(ind[n3:npred], 2, cutoff2, coefs, True, **common)
         return finish(npred)
     mode = 0 if null_model else 1
-    # the slow schedule: n1, a quarter of the rest, the rest -- all cross-validated, maxcor = 2
+    # The slow schedule: n1, a quarter of the rest, the rest -- all cross-validated, maxcor = 2
+    # (R/saver_fit.R:333-462).  The reference runs them as three calc.estimate calls only to print a
+    # finish-time estimate in between; a gene's result depends on its stage through nothing but its
+    # cv seed j = position inside the stage (R/calc_estimate.R:98).  So the three stages go down as
+    # ONE device pass with exactly those seeds: same folds, same results, and the 8-gene first stage
+    # does not cost a whole latency-bound pass of its own.
     n1 = min(max(8, nworkers), npred)
-    msg("Estimating finish time...")
-    fit.run(ind[:n1], mode, 0.0, None, False, **common)
-    if n1 == npred:
-        return finish(n1)
     n2 = min(int(np.ceil((npred - n1) / 4)) + n1, npred)
-    msg("Predicting remaining genes...")
-    fit.run(ind[n1:n2], mode, 0.0, None, False, **common)
-    if n2 == npred:
-        return finish(n2)
-    msg("Predicting remaining genes...")
-    fit.run(ind[n2:npred], mode, 0.0, None, False, **common)
+    seeds = np.concatenate([np.arange(1, b - a + 1) for a, b in ((0, n1), (n1, n2), (n2, npred))])
+    msg("Predicting %d genes (stages of %d, %d, %d)..." % (npred, n1, n2 - n1, npred - n2))
+    fit.run(ind[:npred], mode, 0.0, None, False, seeds=seeds, **common)
     return finish(npred)
 
 
@@ -597,7 +597,7 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
                         plan["pc"], null_model, estimates_only=estimates_only,
                         self_col=plan["self_col"], backend=backend, comm=comm, perm=perm,
                         fold_seed=fold_seed, fold_method=fold_method, nfolds=nfolds,
-                        keep_mu=return_mu, messages=msg, gather=gather)
+                        keep_mu=return_mu, messages=msg, gather=gather, root_design=True)
         gene_names, cell_names = plan["gene_names"], plan["cell_names"]
         sf, scale_sf = plan["sf"], plan["scale_sf"]
         return _saver_result(out, x, sf, scale_sf, gene_names, cell_names, estimates_only,
@@ -658,7 +658,8 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
         out = saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pg, pc, null_model,
                         estimates_only=estimates_only, self_col=self_col, backend=backend,
                         comm=comm, perm=perm, fold_seed=fold_seed, fold_method=fold_method,
-                        nfolds=nfolds, keep_mu=return_mu, messages=msg, counts=dc, gather=gather)
+                        nfolds=nfolds, keep_mu=return_mu, messages=msg, counts=dc, gather=gather,
+                        root_design=root_only)
     msg("Done!")
     return _saver_result(out, x, sf, scale_sf, gene_names, cell_names, estimates_only, return_mu,
                          gather)

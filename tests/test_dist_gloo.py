@@ -35,8 +35,19 @@ def _worker(rank, world, port, outdir):
     # the sharded schedule
     x = synth.nb_counts(90, 50, seed=8).astype(np.float64)
     res = saver_b200.saver(x, do_fast=False, backend=OracleBackend(threads=1), comm=comm, fold_seed=2)
+    # root-only call: only rank 0 holds the matrix (x = None elsewhere); the design and the counts of
+    # the requested genes arrive by broadcast; gather=False leaves every rank with its own rows
+    pg = np.arange(3, 40, 3)
+    be = OracleBackend(threads=1)
+    ro = saver_b200.saver(x if rank == 0 else None, do_fast=False, pred_genes=pg, pred_genes_only=True,
+                          backend=be, comm=comm, fold_seed=2, gather=False)
+    assert be.xest is not None and be.xest.shape[1] == 50        # the broadcast design
+    own = ro.owner == rank
+    assert own.sum() in (pg.size // 2, pg.size - pg.size // 2)
+    assert (ro.estimate[~own] == 0).all() and (ro.estimate[own].sum(1) > 0).any()
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), est=res.estimate, se=res.se,
-             lmin=res.info["lambda.min"], status=res.status)
+             lmin=res.info["lambda.min"], status=res.status, ro_est=ro.estimate, ro_own=own,
+             ro_lmin=ro.info["lambda.min"])
     comm.barrier()
 
 
@@ -145,7 +156,14 @@ def test_two_rank_sharding_is_result_invariant(tmp_path):
     from saver_b200 import synth
     x = synth.nb_counts(90, 50, seed=8).astype(np.float64)
     one = saver_b200.saver(x, do_fast=False, backend=OracleBackend(), fold_seed=2)
+    pg = np.arange(3, 40, 3)
+    sub = saver_b200.saver(x, do_fast=False, pred_genes=pg, pred_genes_only=True, backend=OracleBackend(),
+                           fold_seed=2)
+    merged = np.zeros_like(sub.estimate)
     for r in range(2):
         d = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
         assert np.array_equal(d["est"], one.estimate) and np.array_equal(d["se"], one.se)
         assert np.array_equal(d["lmin"], one.info["lambda.min"])
+        merged[d["ro_own"]] = d["ro_est"][d["ro_own"]]
+        assert np.array_equal(d["ro_lmin"], sub.info["lambda.min"])   # stage scalars reach every rank
+    assert np.array_equal(merged, sub.estimate)                        # the slices tile the one-rank result

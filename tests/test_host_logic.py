@@ -88,11 +88,16 @@ def test_saver_slow_schedule_equals_direct_oracle_calls():
     be = OracleBackend()
     import saver_b200
     res = saver_b200.saver(x, do_fast=False, backend=be, fold_seed=3, return_mu=True, perm="identity")
-    # slow schedule = stages of n1 = 8, ceil((npred-8)/4), rest, all cross-validated; then the rest
+    # slow schedule = stages of n1 = 8, ceil((npred-8)/4), rest, all cross-validated, sent down as
+    # one pass (blocks of the backend's size) with the stage-local seeds; then the null genes
     npred = int((res.x.sum(1) > 0).sum())
     stages = [c for c in be.calls]
-    assert stages[0][:2] == (1, 8) and stages[1][:2] == (1, int(np.ceil((npred - 8) / 4)))
+    assert sum(c[1] for c in stages if c[0] == 1) == npred
     assert all(not c[2] for c in stages)                       # calc.maxcor = FALSE
+    n1, n2 = 8, int(np.ceil((npred - 8) / 4)) + 8
+    pg = np.where(res.x.sum(1) > 0)[0]
+    assert np.array_equal(res.seed_of[pg], np.concatenate([np.arange(1, n1 + 1), np.arange(1, n2 - n1 + 1),
+                                                           np.arange(1, npred - n2 + 1)]))
     assert (res.info["maxcor"][res.x.sum(1) > 0] == 2).all()     # rep(2, .) of R/calc_estimate.R:79
     good = np.where(res.x.mean(1) >= 0.1)[0]
     x_est = np.log((res.x[good] + 1) / res.sf)
