@@ -304,8 +304,19 @@ __global__ void __launch_bounds__(256) lasso_lambda_kernel(RoundArgs A) {
     }
     if (nlam > 2) lam[0] = exp(2.0 * log(lam[1]) - log(lam[2]));
     A.ws.nlam_g[g] = nlam;
-    A.ws.Lfinal[g] = nlam;
   }
+}
+
+// Folds follow their gene's master fit: they stop at its length and never run more than one lambda
+// ahead of its committed path.  Both decisions read this snapshot, taken between rounds, and never
+// the master's live record (master and folds run in the same launch; reading the live record made
+// the amount of work -- though not the result -- depend on CTA scheduling).
+__global__ void lasso_snapshot_kernel(RoundArgs A) {
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  if (g >= A.prm.B) return;
+  const LassoProb& m = A.ws.prob[(size_t)g * A.prm.NF];
+  A.ws.msnap[2 * g] = m.lmu;
+  A.ws.msnap[2 * g + 1] = m.state == ST_DONE ? m.lmu : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -467,11 +478,13 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
       strong_changed = mark_pass(2.0 * al - al0) != 0;
       state = ST_SOLVE;
     }
-  } else if (state == ST_WAIT_KKT) {
-    if (mark_pass(al)) {
+  } else if (state == ST_WAIT_KKT || state == ST_HOLD) {
+    if (state == ST_WAIT_KKT && mark_pass(al)) {
       strong_changed = true;
       state = ST_SOLVE;  // KKT violated outside the strong set: re-solve this lambda
     } else {
+      bool stop = false;
+      if (state == ST_WAIT_KKT) {
       // ---- commit solution lidx ----
       if (fit == 0) {
         const size_t o = (size_t)g * kNLam + lidx;
@@ -487,7 +500,6 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
         A.ws.cvdev[((size_t)g * kNLam + lidx) * kMaxFolds + (fit - 1)] = cur_cv / ncv;
       }
       lmu = lidx + 1;
-      bool stop = false;
       if (master_auto) {
         const int mnl = kMnLam < nlam ? kMnLam : nlam;
         if (lidx + 1 >= mnl) {
@@ -501,13 +513,18 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
           else if (cur_dev > kDevMax) stop = true;
         }
       }
+      }
       int lim = nlam;
+      bool hold = false;
       if (is_fold && A.prm.auto_lambda) {
-        const int lf = *reinterpret_cast<volatile int*>(A.ws.Lfinal + g);
-        if (lf < lim) lim = lf;
+        const int mlmu = A.ws.msnap[2 * g], mdone = A.ws.msnap[2 * g + 1];
+        if (mdone >= 0) { if (mdone < lim) lim = mdone; }
+        else if (lidx + 1 > mlmu + 1) hold = true;  // at most one lambda ahead of the master's path
       }
       if (stop || lidx + 1 >= lim) {
         state = ST_DONE;
+      } else if (hold) {
+        state = ST_HOLD;
       } else {
         ++lidx;
         al0 = al;
@@ -812,7 +829,6 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
     atomicAdd(A.ws.colcount + 1, cyc);   // sum of CTA lifetimes
     atomicMax(A.ws.colcount + 2, cyc);   // longest CTA of the block of rounds (straggler)
     atomicAdd(A.ws.colcount + 3, (unsigned long long)(state == ST_WAIT_KKT || state == ST_DONE));
-    if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
     PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
     PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
     PR->al = al; PR->al0 = al0; PR->az = az; PR->v0 = v0; PR->sumr = sumr;
@@ -1423,11 +1439,13 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       strong_changed = mark_pass(2.0 * al - al0) != 0;
       state = ST_SOLVE;
     }
-  } else if (state == ST_WAIT_KKT) {
-    if (mark_pass(al)) {
+  } else if (state == ST_WAIT_KKT || state == ST_HOLD) {
+    if (state == ST_WAIT_KKT && mark_pass(al)) {
       strong_changed = true;
       state = ST_SOLVE;  // KKT violated outside the strong set: re-solve this lambda
     } else {
+      bool stop = false;
+      if (state == ST_WAIT_KKT) {
       // ---- commit solution lidx ----
       if (fit == 0) {
         const size_t o = (size_t)g * kNLam + lidx;
@@ -1443,7 +1461,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         A.ws.cvdev[((size_t)g * kNLam + lidx) * kMaxFolds + (fit - 1)] = cur_cv / ncv;
       }
       lmu = lidx + 1;
-      bool stop = false;
       if (master_auto) {
         const int mnl = kMnLam < nlam ? kMnLam : nlam;
         if (lidx + 1 >= mnl) {
@@ -1457,13 +1474,18 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
           else if (cur_dev > kDevMax) stop = true;
         }
       }
+      }
       int lim = nlam;
-      if (is_fold && A.prm.auto_lambda) {
-        const int lf = *reinterpret_cast<volatile int*>(A.ws.Lfinal + g);
-        if (lf < lim) lim = lf;
+      bool hold = false;
+      if (is_fold && A.prm.auto_lambda && !(A.prm.dbg & 8192)) {  // bit 8192: folds ignore the master (fault hunting)
+        const int mlmu = A.ws.msnap[2 * g], mdone = A.ws.msnap[2 * g + 1];
+        if (mdone >= 0) { if (mdone < lim) lim = mdone; }
+        else if (lidx + 1 > mlmu + 1) hold = true;  // at most one lambda ahead of the master's path
       }
       if (stop || lidx + 1 >= lim) {
         state = ST_DONE;
+      } else if (hold) {
+        state = ST_HOLD;
       } else {
         ++lidx;
         al0 = al;
@@ -1507,6 +1529,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // p_l = sum w Xs_l -> swa[l], r_l = sum wr Xs_l -> gq[l]   (four columns per reduction)
   // (one warp per column, independent accumulators per lane, no block barrier inside)
   auto gram_vectors = [&](int l0, int l1, bool with_p) {
+    crumb_m = l1;
+    crumb(17);
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
     if (mlp) {
       for (int lb = l0 + 4 * warp; lb < l1; lb += 4 * nw) {
@@ -1549,6 +1573,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   };
   // raw weighted Gram P[l][k] = sum_i w_i Xs_il Xs_ik for l, k < m, 16 x 16 tiles per warp on DMMA
   auto gram_P = [&](int m) {
+    crumb_m = m;
+    crumb(16);
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5, g8 = lane >> 2, t4 = lane & 3;
     const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2;
     for (int tix = warp; tix < ntile; tix += nw) {
@@ -1696,8 +1722,11 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     tph[8] += m;
     tph[9] += 1;
     if (timing && tid == 0) atomicAdd(A.ws.phasecyc + 16 + (m - 1) / 32, (unsigned long long)m);
+    crumb_m = m;
+    crumb(m <= 384 ? (hs_m == m ? 11 : 12) : 13);
     if (m <= 384) gsweep_warp(by_index, m, dlx);
     else gsweep_block(by_index, m, dlx);
+    crumb(14);
   };
   auto gintercept = [&](int m, double& dlx) {
     const double d = q0 / v0m;
@@ -1711,6 +1740,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // bring the n-space residual up to date with the coefficients: wr -= w * (X~_A da + daz)
   auto materialise = [&](int m) {
     if (!dirty) return;
+    crumb_m = m;
+    crumb(18);
     double sh[1] = {0.0};
     for (int l = tid; l < m; l += T) {
       const double c = (aact[l] - amat[l]) * xia[l];
@@ -1854,9 +1885,14 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // Strong-set check of the inactive variables (KKT inside the strong set): g_k = x~_k^T wr for a
   // staged chunk of candidates, one warp per column; the first variable (in index order) whose
   // |g_k| exceeds lambda enters, after which the rest of the chunk is evaluated again.
-  auto inactive_check = [&](int& m, double& dlx, bool& overflow) {
+  // full = false: only the candidates whose last known |g_k| came within 20 % of lambda are looked at
+  // again (the later passes of one IRLS step move the coefficients by convergence-sized steps; a
+  // candidate that slips through is caught by the full pass that opens the next IRLS step, or by the
+  // KKT check over all predictors that follows the solve).  GL = last |g_k| per candidate, kept in
+  // the problem's gradient column, which phase A has finished with.
+  double* GL = const_cast<double*>(Gc);
+  auto inactive_check = [&](int& m, double& dlx, bool& overflow, bool full) {
     if (ninact == 0) return;
-    tph[10] += ninact;
     tph[11] += 1;
     materialise(m);
     lap(4);
@@ -1870,10 +1906,14 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         mk[tid] = k;
         mxm[tid] = XMc[k];
         mxi[tid] = XIc[k];
-        mpos[tid] = MMc[k];
+        int mp = MMc[k];
+        if (!full && mp < 0 && GL[cur + tid] < 0.8 * al) mp = 0;  // skipped in this pass
+        mpos[tid] = mp;
       }
       __syncthreads();
       int j0 = 0;
+      crumb_m = cur;
+      crumb(15);
       while (j0 < cn) {
         if (mlp) {
           for (int jb = j0 + 4 * warp; jb < cn; jb += 4 * nw) {
@@ -1894,7 +1934,11 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             if (lane == 0) {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                if (need[c]) mg[jb + c] = mxi[jb + c] * (acc4[c] - mxm[jb + c] * q0);
+                if (need[c]) {
+                  const double gv = mxi[jb + c] * (acc4[c] - mxm[jb + c] * q0);
+                  mg[jb + c] = gv;
+                  GL[cur + jb + c] = fabs(gv);
+                }
             }
           }
         } else {
@@ -1910,7 +1954,10 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
                 s1 += r.y * x.y;
               }
               const double acc = warp_sum(s0 + s1);
-              if (lane == 0) mg[j] = mxi[j] * (acc - mxm[j] * q0);
+              if (lane == 0) {
+                mg[j] = mxi[j] * (acc - mxm[j] * q0);
+                GL[cur + j] = fabs(mg[j]);
+              }
             }
           }
         }
@@ -1919,6 +1966,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         for (int j = j0; j < cn; ++j)
           if (mpos[j] < 0) {
             ++ncols;
+            tph[10] += 1;
             if (fabs(mg[j]) > al) { hit = j; break; }
           }
         if (hit < 0) break;
@@ -2011,6 +2059,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       tph[12] += m;
       crumb_m = m;
       crumb(4);
+      bool first_pass = true;  // the first strong-set check of an IRLS step looks at every candidate
       while (true) {  // strong-set phases until one changes nothing
         ++nlp;
         double dlx = 0.0;
@@ -2019,7 +2068,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         lap(4);
         crumb_m = m;
         crumb(6);
-        if (!(dbg & 8)) inactive_check(m, dlx, overflow);
+        if (!(dbg & 8)) inactive_check(m, dlx, overflow, first_pass || (dbg & 16384));
+        first_pass = false;
         crumb_m = m;
         crumb(5);
         lap(5);
@@ -2172,7 +2222,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     atomicAdd(A.ws.colcount + 1, cyc);   // sum of CTA lifetimes
     atomicMax(A.ws.colcount + 2, cyc);   // longest CTA of the block of rounds (straggler)
     atomicAdd(A.ws.colcount + 3, (unsigned long long)(state == ST_WAIT_KKT || state == ST_DONE));
-    if (fit == 0 && state == ST_DONE) A.ws.Lfinal[g] = lmu;  // the folds stop at the master's length
     PR->state = state; PR->lidx = lidx; PR->lmu = lmu; PR->nin = nin; PR->nS = nS;
     PR->jerr = jerr; PR->nlp = nlp; PR->ngrad += 1;
     PR->al = al; PR->al0 = al0; PR->az = az; PR->v0 = v0; PR->sumr = sumr;
@@ -2207,8 +2256,10 @@ __global__ void __launch_bounds__(256) lasso_finalize_kernel(FinalArgs F) {
   if (A.ws.gstat[g]) st = 1;
   int L = P0->lmu;
   if (!st) {
+    // a fold fit may have been one lambda past the master's path when the master stopped: a fatal
+    // error there (lidx >= L) concerns a solution cv.glmnet never asks for
     for (int f = 0; f < NF; ++f)
-      if (P0[f].jerr > 0 || P0[f].lmu < 1) st = 2;
+      if ((P0[f].jerr > 0 && (f == 0 || P0[f].lidx < L)) || P0[f].lmu < 1) st = 2;
   }
   if (F.stats && tid == 0) {
     int nlp = 0, ngr = 0;
@@ -2422,7 +2473,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oMM = take((size_t)p_pad * P * 4), oSI = take((size_t)p_pad * P * 4),
                oIA = take((size_t)kNX * P * 4), oAA = take((size_t)kNX * P * 8), oAS = take((size_t)kNX * P * 8),
                oPR = take(sizeof(LassoProb) * (size_t)P), oLam = take((size_t)kNLam * B * 8),
-               oNl = take((size_t)B * 4), oLf = take((size_t)B * 4), oGs = take((size_t)B * 4),
+               oNl = take((size_t)B * 4), oLf = take((size_t)B * 8), oGs = take((size_t)B * 4),
                oGm = take((size_t)B * 8), oA0 = take((size_t)kNLam * B * 8),
                oDv = take((size_t)kNLam * B * 8), oNi = take((size_t)kNLam * B * 4), oNp = take((size_t)kNLam * B * 4),
                oCap = take((size_t)kNX * kNLam * B * 8),
@@ -2447,7 +2498,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   ws.G = (double*)(b + oG); ws.XM = (double*)(b + oXM); ws.XI = (double*)(b + oXI);
   ws.MM = (int*)(b + oMM); ws.SIDX = (int*)(b + oSI); ws.IA = (int*)(b + oIA);
   ws.AACT = (double*)(b + oAA); ws.AS = (double*)(b + oAS); ws.prob = (LassoProb*)(b + oPR); ws.lam = (double*)(b + oLam);
-  ws.nlam_g = (int*)(b + oNl); ws.Lfinal = (int*)(b + oLf); ws.gstat = (int*)(b + oGs);
+  ws.nlam_g = (int*)(b + oNl); ws.msnap = (int*)(b + oLf); ws.gstat = (int*)(b + oGs);
   ws.gmean = (double*)(b + oGm); ws.a0p = (double*)(b + oA0); ws.devp = (double*)(b + oDv);
   ws.ninp = (int*)(b + oNi); ws.nlpp = (int*)(b + oNp); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
   ws.list0 = (int*)(b + oL0); ws.list1 = (int*)(b + oL1); ws.counters = (int*)(b + oCt);
@@ -2494,7 +2545,6 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   } else {
     if ((e = cudaMemcpyAsync(ws.lam, lam_user, (size_t)kNLam * B * 8, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(ws.nlam_g, nlam_user, (size_t)B * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(ws.Lfinal, nlam_user, (size_t)B * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
@@ -2507,7 +2557,9 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   bool gram = prm.gram != 0;
   if (tune.gram >= 0) gram = tune.gram != 0;
   int T = ldx <= 2048 ? 128 : ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
-  if (gram) T = ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
+  // Gram kernel: 256 threads (two CTAs per SM) while W / WR fit twice; 512 above -- never 1,024: at 64
+  // registers per thread the streaming helpers spill and the kernel runs 25 % slower (profiles/r2_cfg3_cta_size.log)
+  if (gram) T = ldx <= 4096 ? 256 : 512;
   if (gram && tune.gram_threads > 0) T = tune.gram_threads;
   if (tune.threads > 0) T = tune.threads;  // tuning experiments only
   if (T != 128 && T != 256 && T != 512 && T != 1024) return cudaErrorInvalidValue;
@@ -2578,6 +2630,10 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     int* next = cur ? ws.list0 : ws.list1;
     int* cnt = ws.counters + (cur ? 0 : 1);
     if ((e = cudaMemsetAsync(cnt, 0, 4, s)) != cudaSuccess) return e;
+    if (prm.auto_lambda) {
+      lasso_snapshot_kernel<<<(B + 255) / 256, 256, 0, s>>>(A);
+      *launches += 1;
+    }
     cudaEventRecord(ws.ev[0], s);
     A.round_no = rounds;
     if (gram) {

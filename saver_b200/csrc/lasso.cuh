@@ -9,7 +9,9 @@ constexpr int kNLam = 128;   // capacity of a lambda sequence (glmnet nlambda = 
 constexpr int kMaxFolds = 16;
 constexpr int kCrumbSlots = 16384;
 
-enum ProbState : int { ST_INIT = 0, ST_SOLVE = 1, ST_WAIT_KKT = 2, ST_DONE = 3 };
+// ST_HOLD: a fold fit that would get more than one lambda ahead of its gene's master fit waits (it
+// keeps its place in the problem list and is looked at again next round).
+enum ProbState : int { ST_INIT = 0, ST_SOLVE = 1, ST_WAIT_KKT = 2, ST_DONE = 3, ST_HOLD = 4 };
 
 // One (gene, fit) problem: fit 0 = master fit on all pred cells, fit f > 0 = CV fold f held out.
 struct LassoProb {
@@ -86,7 +88,9 @@ struct LassoWs {
   double *AS;                // kNX x P coefficients at the start of the current IRLS step (gram kernel)
   LassoProb* prob;           // P
   double *lam;               // kNLam x B
-  int *nlam_g, *Lfinal, *gstat;   // B
+  int *nlam_g, *gstat;       // B
+  int *msnap;                // 2 x B: the master fit's committed count and (when done) its final length,
+                             // as of the START of the round -- what the fold fits steer by
   double *gmean;             // B: mean of y over the pred cells
   double *a0p, *devp;        // kNLam x B master path
   int *ninp;                 // kNLam x B

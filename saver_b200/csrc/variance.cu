@@ -40,24 +40,37 @@ struct Gene {
   double* scratch;      // block reduction scratch
 };
 
+// lgamma(y + al) - lgamma(al) for a cell with y != 0.  For the integer counts the path sees this is
+// log prod_{j < y} (al + j): one log instead of two lgamma calls, and without the cancellation of
+// two large lgamma values (the reference's own arithmetic loses ~1e-7 absolute there when al is
+// large).  Non-integer y, y > 32 or a product that could overflow fall back to the lgamma pair.
+__device__ __forceinline__ double lgamma_diff(double y, double al) {
+  if (y <= 32.0 && y == floor(y) && al < 1.0e9) {
+    double pr = al;
+    for (double j = 1.0; j < y; j += 1.0) pr *= al + j;
+    return log(pr);
+  }
+  return lgamma(y + al) - lgamma(al);
+}
+
 // -calc.loglik.{a,b,k}(param): identical on every thread.
 __device__ double loglik(int model, double prm, const Gene& g) {
   const int n = g.n;
   if (model == 0) {
     // R/calc_loglik.R:34-39
     const double ia = 1.0 / prm;
-    double acc[2] = {0.0, 0.0};  // sum lgamma(y+1/a) over y!=0 ; sum (y+1/a) log(sf + 1/(a mu))
-    for (int t = threadIdx.x; t < g.nnz; t += kThreads) acc[0] += lgamma(g.y[g.nz[t]] + ia);
+    double acc[2] = {0.0, 0.0};  // sum [lgamma(y+1/a) - lgamma(1/a)] over y!=0 ; sum (y+1/a) log(sf + 1/(a mu))
+    for (int t = threadIdx.x; t < g.nnz; t += kThreads) acc[0] += lgamma_diff(g.y[g.nz[t]], ia);
     for (int i = threadIdx.x; i < n; i += kThreads)
       acc[1] += (g.y[i] + ia) * log(g.sf[i] + 1.0 / (prm * g.mu[i]));
     block_sum<2>(acc, g.scratch);
-    const double lg = lgamma(ia);
     const double f1 = n / prm * log(ia);
     const double f2 = -(ia * g.sum_logmu);
-    const double f3 = -n * lg;
-    const double f4 = acc[0] + (double)(n - g.nnz) * lg;
+    // f3 + f4 of R/calc_loglik.R:36-37 = -n lgamma(1/a) + sum lgamma(y + 1/a): the cells with y == 0
+    // cancel exactly, the others are the differences accumulated above
+    const double f34 = acc[0];
     const double f5 = -acc[1];
-    return -(f1 + f2 + f3 + f4 + f5);
+    return -(f1 + f2 + f34 + f5);
   }
   if (model == 1) {
     // R/calc_loglik.R:52-56
@@ -66,7 +79,7 @@ __device__ double loglik(int model, double prm, const Gene& g) {
     for (int t = threadIdx.x; t < g.nnz; t += kThreads) {
       const int i = g.nz[t];
       const double mb = g.mu[i] / prm;
-      acc[1] += lgamma(g.y[i] + mb) - lgamma(mb);
+      acc[1] += lgamma_diff(g.y[i], mb);
     }
     for (int i = threadIdx.x; i < n; i += kThreads) {
       const double mb = g.mu[i] / prm;
@@ -82,7 +95,7 @@ __device__ double loglik(int model, double prm, const Gene& g) {
   for (int t = threadIdx.x; t < g.nnz; t += kThreads) {
     const int i = g.nz[t];
     const double m = g.mu[i], mk = m * m / prm;
-    acc[1] += lgamma(g.y[i] + mk) - lgamma(mk);
+    acc[1] += lgamma_diff(g.y[i], mk);
   }
   for (int i = threadIdx.x; i < n; i += kThreads) {
     const double m = g.mu[i], m2 = m * m;
@@ -91,6 +104,74 @@ __device__ double loglik(int model, double prm, const Gene& g) {
   }
   block_sum<3>(acc, g.scratch);
   return -(g.sum_mu2logmu / prm - acc[0] + acc[1] - acc[2]);
+}
+
+// The 100-point grid of the fallback branch (R/optimize_variance.R:46-52) as ONE pass: the
+// parameters are known up front, so warp w takes grid points w, w + 8, ... (13 per warp, their
+// accumulators in registers) and streams over all cells; no block barrier until the end.  Per point
+// the sums run over the same cells with the same per-cell expressions as loglik(), in a different
+// association order (per-lane strided partial sums), i.e. they agree with it to rounding.
+// out[i] = -nll(x_i) for i < 100 (every thread reads them from shared memory afterwards).
+constexpr int kGridPts = 100;
+constexpr int kGridPerWarp = (kGridPts + kNW - 1) / kNW;
+
+__device__ void loglik_grid(int model, const double* xs, const Gene& g, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g.n;
+  double prm[kGridPerWarp], c1[kGridPerWarp], acc[kGridPerWarp];
+#pragma unroll
+  for (int q = 0; q < kGridPerWarp; ++q) {
+    const int i = warp + q * kNW;
+    prm[q] = xs[i < kGridPts ? i : kGridPts - 1];
+    c1[q] = model == 0 ? 1.0 / prm[q] : model == 1 ? 1.0 / prm[q] : prm[q];
+    acc[q] = 0.0;
+  }
+  for (int t = lane; t < g.nnz; t += 32) {
+    const int i = g.nz[t];
+    const double y = g.y[i], m = g.mu[i];
+#pragma unroll
+    for (int q = 0; q < kGridPerWarp; ++q) {
+      const double al = model == 0 ? c1[q] : model == 1 ? m / prm[q] : m * m / prm[q];
+      acc[q] += lgamma_diff(y, al);
+    }
+  }
+  if (model == 0) {
+    for (int i = lane; i < n; i += 32) {
+      const double y = g.y[i], m = g.mu[i], sfi = g.sf[i];
+#pragma unroll
+      for (int q = 0; q < kGridPerWarp; ++q) acc[q] -= (y + c1[q]) * log(sfi + 1.0 / (prm[q] * m));
+    }
+  } else if (model == 1) {
+    double lib[kGridPerWarp];
+#pragma unroll
+    for (int q = 0; q < kGridPerWarp; ++q) lib[q] = log(c1[q]);
+    for (int i = lane; i < n; i += 32) {
+      const double y = g.y[i], m = g.mu[i], sfi = g.sf[i];
+#pragma unroll
+      for (int q = 0; q < kGridPerWarp; ++q) {
+        const double mb = m / prm[q];
+        acc[q] += mb * lib[q] - (y + mb) * log(sfi + c1[q]);
+      }
+    }
+  } else {
+    double lk[kGridPerWarp];
+#pragma unroll
+    for (int q = 0; q < kGridPerWarp; ++q) lk[q] = log(prm[q]);
+    for (int i = lane; i < n; i += 32) {
+      const double y = g.y[i], m = g.mu[i], sfi = g.sf[i], m2 = m * m;
+#pragma unroll
+      for (int q = 0; q < kGridPerWarp; ++q)
+        acc[q] -= m2 * lk[q] / prm[q] + (y + m2 / prm[q]) * log(sfi + m / prm[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kGridPerWarp; ++q) {
+    double v = warp_sum(acc[q]);
+    const int i = warp + q * kNW;
+    if (model == 0) v += n / prm[q] * log(c1[q]) - c1[q] * g.sum_logmu;
+    else if (model == 2) v += g.sum_mu2logmu / prm[q];
+    if (lane == 0 && i < kGridPts) out[i] = v;
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ double guard(double v) { return isfinite(v) ? v : DBL_MAX; }
@@ -236,19 +317,19 @@ __device__ FitResult fit_model(int model, double upper, const Gene& g, double* g
       // samp = (exp((exp(ppoints(100)) - 1)/2) - 1) * gmax ; weights exp(ll - min ll)
       double llmin = INFINITY;
       bool bad = false;
+      __syncthreads();  // grid_s may still be read by the previous model's epilogue
+      if (threadIdx.x < 100) {
+        const double pp = (threadIdx.x + 1 - 0.5) / 100.0;
+        grid_s[threadIdx.x] = (exp((exp(pp) - 1) / 2) - 1) * gmax;
+      }
+      __syncthreads();
+      loglik_grid(model, grid_s, g, grid_s + 100);
       for (int i = 0; i < 100; ++i) {
-        const double pp = (i + 1 - 0.5) / 100.0;
-        const double sx = (exp((exp(pp) - 1) / 2) - 1) * gmax;
-        const double ll = -loglik(model, sx, g);
-        if (threadIdx.x == 0) {
-          grid_s[i] = sx;
-          grid_s[100 + i] = ll;
-        }
+        const double ll = grid_s[100 + i];
         if (ll < llmin) llmin = ll;
         if (isnan(ll)) bad = true;
       }
       r.nev += 100;
-      __syncthreads();
       if (grid_out && threadIdx.x < 200) grid_out[threadIdx.x] = grid_s[threadIdx.x];
       if (bad) err = true;
       else {
