@@ -460,6 +460,15 @@ def run_cuda(args):
         "status_counts": np.bincount(status_res, minlength=3).tolist(),
         "host_s_timed_region": t_host, "setup_s": t_setup,
     }
+    if int(os.environ.get("SAVER_LASSO_DBG", "0")) & 128:   # per-phase SM cycles of the round kernel (diagnostic)
+        ph = np.zeros(16)
+        h.lib.saver_cuda_phase_cycles(h.h, ops.ptr(ph))
+        names = ["phaseA", "vectors", "gramP", "sweeps", "material", "inactive", "relin"]
+        tot = ph[:7].sum() + ph[13]
+        line["phases"] = {k: round(float(v / tot), 4) for k, v in zip(names, ph[:7])}
+        line["phases"].update(activate=round(float(ph[13] / tot), 4), irls_per_gene=float(ph[7] / max(1, B * (args.steps + args.warmup))),
+                              mean_m=float(ph[12] / max(ph[7], 1)), inactive_cols_per_irls=float(ph[10] / max(ph[7], 1)),
+                              activations_per_irls=float(ph[14] / max(ph[7], 1)), sweep_steps_per_irls=float(ph[8] / max(ph[7], 1)))
     if parity is not None:
         line["parity"] = parity
     if cpu is not None and world == 1:

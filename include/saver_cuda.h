@@ -189,6 +189,19 @@ SAVER_API int saver_cuda_csc_sums(saver_cuda_handle h, double* col_sums, double*
 SAVER_API int saver_cuda_csc_gather(saver_cuda_handle h, const int* gene_idx, int B, const double* sf,
                                     int transform, double* out, int out_on_device);
 
+/* ---- dense counts: R's plain matrix, the hot path's a1-a3 (R/saver.R:105-157, R/utils.R:2-31,70-86) ----
+ * x: genes x cells as G contiguous rows of n cells (= t(x) column-major, the panel layout), dtype 0 =
+ * double, 1 = int32 (host pointer).  Uploaded once and kept resident until replaced or released;
+ * values < 0.001 read as 0 (clean.data, R/utils.R:11-19).  The sums feed calc.size.factor
+ * (R/utils.R:72), the rowMeans >= 0.1 filter (R/saver.R:156) and get.pred.genes; the gather with
+ * transform = 1 is x.est = log((x[good, ] + 1) / sf) (R/saver.R:157) written straight into a device
+ * panel for saver_cuda_set_design, so the design never exists on the host. */
+SAVER_API int saver_cuda_set_counts_dense(saver_cuda_handle h, const void* x, int dtype, int G, int n);
+SAVER_API int saver_cuda_dense_sums(saver_cuda_handle h, double* col_sums, double* row_sums);
+SAVER_API int saver_cuda_dense_gather(saver_cuda_handle h, const int* gene_idx, int B, const double* sf,
+                                      int transform, double* out, int out_on_device);
+SAVER_API int saver_cuda_release_counts(saver_cuda_handle h);
+
 /* Problem columns pushed through the gradient GEMM so far (roofline accounting in bench.py):
  * every column is one 2 * n * p flop contraction against the resident design. */
 SAVER_API long long saver_cuda_gemm_columns(saver_cuda_handle h);

@@ -121,6 +121,19 @@ saver.cuda.log.rows <- function(genes, sf)
   .Call(C_saver_cuda_csc_gather, saver.cuda.handle(), as.integer(genes - 1L), as.numeric(sf),
         length(sf))
 
+# dense input (matrix): one upload of t(x); colSums / rowMeans / x.est come back from the device, so
+# saver() (R/saver.R:105-157) never makes its three host passes over the whole matrix:
+#   d <- saver.cuda.set.dense(x); sf <- d$col.sums / mean(d$col.sums)
+#   good.genes <- which(d$row.sums / ncol(x) >= 0.1); x.est <- saver.cuda.dense.log.rows(good.genes, sf)
+saver.cuda.set.dense <- function(x) {
+  .Call(C_saver_cuda_set_counts_dense, saver.cuda.handle(), t(x))
+  sums <- .Call(C_saver_cuda_dense_sums, saver.cuda.handle(), dim(x))
+  list(col.sums = sums[[1]], row.sums = sums[[2]], ncells = ncol(x))
+}
+saver.cuda.dense.log.rows <- function(genes, sf)
+  .Call(C_saver_cuda_dense_gather, saver.cuda.handle(), as.integer(genes - 1L), as.numeric(sf),
+        length(sf))
+
 # saver(), saver.fit(), saver.fit.mean/.null, get.mu, combine.saver and R/utils.R stay as they are
 # in the reference (they only call the functions above); saver() forces ncores to one process:
 #   if (ncores > 1) message("libsaver_cuda: device parallelism replaces ", ncores, " PSOCK workers")

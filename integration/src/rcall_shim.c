@@ -223,6 +223,46 @@ SEXP C_saver_cuda_csc_gather(SEXP hp, SEXP genes0, SEXP sf, SEXP ncells)
     return out;
 }
 
+/* dense counts: x is the R matrix t(x) (cells x genes, so one gene is one contiguous column); double
+ * or integer storage.  Replaces the whole-matrix passes of R/saver.R:105-157 (see saver_cuda.R). */
+SEXP C_saver_cuda_set_counts_dense(SEXP hp, SEXP xt)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_nrows(xt), G = Rf_ncols(xt);
+    if (Rf_isInteger(xt))
+        check(h, saver_cuda_set_counts_dense(h, int_arg(xt, (R_xlen_t)n * G, "t(x)"), 1, G, n));
+    else
+        check(h, saver_cuda_set_counts_dense(h, real_arg(xt, (R_xlen_t)n * G, "t(x)"), 0, G, n));
+    return R_NilValue;
+}
+
+SEXP C_saver_cuda_dense_sums(SEXP hp, SEXP dim)
+{
+    saver_cuda_handle h = get_handle(hp);
+    int *pd = int_arg(dim, 2, "dim");
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP cs = PROTECT(Rf_allocVector(REALSXP, pd[1]));
+    SEXP rs = PROTECT(Rf_allocVector(REALSXP, pd[0]));
+    check(h, saver_cuda_dense_sums(h, REAL(cs), REAL(rs)));
+    SET_VECTOR_ELT(out, 0, cs);
+    SET_VECTOR_ELT(out, 1, rs);
+    UNPROTECT(3);
+    return out;
+}
+
+/* t(log((x[genes, ] + 1) / sf)) (n x B) from the resident dense counts */
+SEXP C_saver_cuda_dense_gather(SEXP hp, SEXP genes0, SEXP sf, SEXP ncells)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int B = Rf_length(genes0), n = Rf_asInteger(ncells);
+    int *pg = int_arg(genes0, B, "genes");
+    double *psf = Rf_isNull(sf) ? NULL : real_arg(sf, n, "sf");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, B));
+    check(h, saver_cuda_dense_gather(h, pg, B, psf, psf != NULL, REAL(out), 0));
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_saver_cuda_create", (DL_FUNC)&C_saver_cuda_create, 1},
     {"C_saver_cuda_set_design", (DL_FUNC)&C_saver_cuda_set_design, 2},
@@ -236,6 +276,9 @@ static const R_CallMethodDef call_methods[] = {
     {"C_saver_cuda_set_counts_csc", (DL_FUNC)&C_saver_cuda_set_counts_csc, 5},
     {"C_saver_cuda_csc_sums", (DL_FUNC)&C_saver_cuda_csc_sums, 2},
     {"C_saver_cuda_csc_gather", (DL_FUNC)&C_saver_cuda_csc_gather, 4},
+    {"C_saver_cuda_set_counts_dense", (DL_FUNC)&C_saver_cuda_set_counts_dense, 2},
+    {"C_saver_cuda_dense_sums", (DL_FUNC)&C_saver_cuda_dense_sums, 2},
+    {"C_saver_cuda_dense_gather", (DL_FUNC)&C_saver_cuda_dense_gather, 4},
     {NULL, NULL, 0}};
 
 void R_init_SAVERcuda(DllInfo* dll)

@@ -25,6 +25,9 @@ struct saver_cuda_ctx {
   int *csc_indptr = nullptr, *csc_indices = nullptr, *csc_map = nullptr;
   double* csc_data = nullptr;
   int csc_G = 0, csc_n = 0;
+  // resident dense counts (sparse.cu): G rows of n cells, double (dtype 0) or int32 (dtype 1)
+  void* dn_x = nullptr;
+  int dn_dtype = 0, dn_G = 0, dn_n = 0;
 };
 
 inline int fail(saver_cuda_ctx* h, int code, const char* fmt, ...) {

@@ -1885,13 +1885,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // Strong-set check of the inactive variables (KKT inside the strong set): g_k = x~_k^T wr for a
   // staged chunk of candidates, one warp per column; the first variable (in index order) whose
   // |g_k| exceeds lambda enters, after which the rest of the chunk is evaluated again.
-  // full = false: only the candidates whose last known |g_k| came within 20 % of lambda are looked at
-  // again (the later passes of one IRLS step move the coefficients by convergence-sized steps; a
-  // candidate that slips through is caught by the full pass that opens the next IRLS step, or by the
-  // KKT check over all predictors that follows the solve).  GL = last |g_k| per candidate, kept in
-  // the problem's gradient column, which phase A has finished with.
-  double* GL = const_cast<double*>(Gc);
-  auto inactive_check = [&](int& m, double& dlx, bool& overflow, bool full) {
+  auto inactive_check = [&](int& m, double& dlx, bool& overflow) {
     if (ninact == 0) return;
     tph[11] += 1;
     materialise(m);
@@ -1906,9 +1900,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         mk[tid] = k;
         mxm[tid] = XMc[k];
         mxi[tid] = XIc[k];
-        int mp = MMc[k];
-        if (!full && mp < 0 && GL[cur + tid] < 0.8 * al) mp = 0;  // skipped in this pass
-        mpos[tid] = mp;
+        mpos[tid] = MMc[k];
       }
       __syncthreads();
       int j0 = 0;
@@ -1934,11 +1926,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
             if (lane == 0) {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                if (need[c]) {
-                  const double gv = mxi[jb + c] * (acc4[c] - mxm[jb + c] * q0);
-                  mg[jb + c] = gv;
-                  GL[cur + jb + c] = fabs(gv);
-                }
+                if (need[c]) mg[jb + c] = mxi[jb + c] * (acc4[c] - mxm[jb + c] * q0);
             }
           }
         } else {
@@ -1954,10 +1942,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
                 s1 += r.y * x.y;
               }
               const double acc = warp_sum(s0 + s1);
-              if (lane == 0) {
-                mg[j] = mxi[j] * (acc - mxm[j] * q0);
-                GL[cur + j] = fabs(mg[j]);
-              }
+              if (lane == 0) mg[j] = mxi[j] * (acc - mxm[j] * q0);
             }
           }
         }
@@ -2059,7 +2044,6 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       tph[12] += m;
       crumb_m = m;
       crumb(4);
-      bool first_pass = true;  // the first strong-set check of an IRLS step looks at every candidate
       while (true) {  // strong-set phases until one changes nothing
         ++nlp;
         double dlx = 0.0;
@@ -2068,8 +2052,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         lap(4);
         crumb_m = m;
         crumb(6);
-        if (!(dbg & 8)) inactive_check(m, dlx, overflow, first_pass || (dbg & 16384));
-        first_pass = false;
+        if (!(dbg & 8)) inactive_check(m, dlx, overflow);
         crumb_m = m;
         crumb(5);
         lap(5);

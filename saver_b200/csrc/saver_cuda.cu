@@ -61,6 +61,7 @@ int saver_cuda_destroy(saver_cuda_handle h) {
   h->design.release();
   h->lasso.release();
   cudaFree(h->csc_indptr); cudaFree(h->csc_indices); cudaFree(h->csc_data); cudaFree(h->csc_map);
+  cudaFree(h->dn_x);
   cudaStreamDestroy(h->stream);
   delete h;
   return SAVER_OK;

@@ -207,6 +207,12 @@ class CudaBackend:
         ops.set_counts_csc(x, handle=self.handle)
         return DeviceCounts(x, self.handle)
 
+    def load_dense(self, x):
+        """Dense input (R: matrix): upload once; clean.data's threshold, colSums / rowMeans and the
+        log-normalised design are then computed on the device (saver_cuda_set_counts_dense)."""
+        ops.set_counts_dense(x, handle=self.handle)
+        return DenseDeviceCounts(x, self.handle)
+
     def calc_estimate(self, x, sf, scale_sf, mode, cutoff=0.0, coefs=None, self_col=None,
                       is_pred=None, pred_mask=None, foldid=None, nfolds=5, calc_maxcor=False,
                       estimates_only=False, want_mu=False, dfmax=300, nlambda=100, thresh=1e-7):
@@ -294,12 +300,31 @@ class DeviceCounts:
         return ops.csc_gather(rows, sf=sf, transform=True, device=True, handle=self.handle)
 
 
+class DenseDeviceCounts:
+    """A dense count matrix resident on the device (csrc/sparse.cu, dense part): the whole-matrix
+    passes of saver() -- x[x < 0.001] <- 0, colSums, rowMeans, x.est (R/utils.R:11-19,72,
+    R/saver.R:156-157) -- without a host copy of the matrix or of the design."""
+
+    def __init__(self, x, handle):
+        self.shape = x.shape
+        self.handle = handle
+        self.col_sums, self.row_sums = ops.dense_sums(handle=handle)
+
+    def log_rows(self, rows, sf):
+        return ops.dense_gather(rows, sf=sf, transform=True, device=True, handle=self.handle)
+
+    def release(self):
+        ops.release_counts(handle=self.handle)
+
+
 def _dense_rows(x, rows, dc=None):
     if dc is not None:
         return dc.rows(rows)
     if hasattr(x, "tocsc"):
         return np.asarray(x.tocsr()[rows].todense(), dtype=np.float64)
-    return np.ascontiguousarray(x[rows], dtype=np.float64)
+    xb = np.array(x[rows], dtype=np.float64)   # a copy: clean.data's threshold (a no-op on a cleaned x)
+    xb[xb < 0.001] = 0
+    return xb
 
 
 class _Fit:
@@ -395,7 +420,7 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
               ngenes=None, ncells=None, gene_names=None, cell_names=None, estimates_only=False,
               *, self_col=None, backend=None, comm=None, perm=None, fold_seed=0,
               fold_method="philox", nfolds=5, keep_mu=False, messages=None, gather=True,
-              counts=None, root_design=False):
+              counts=None, root_design=False, row_sums=None):
     """saver.fit (R/saver_fit.R:56-463): the stage schedule.
 
     x (genes x cells counts), x_est ((p, n) = t(x.est) of R/saver.R:157, gene-major),
@@ -419,6 +444,8 @@ def saver_fit(x, x_est, do_fast, ncores, sf, scale_sf, pred_genes, pred_cells, n
     pred_genes = np.asarray(pred_genes, dtype=np.int64)
     if counts is not None:
         rs = counts.row_sums[pred_genes]
+    elif row_sums is not None:
+        rs = np.asarray(row_sums)[pred_genes]
     else:
         rs = np.asarray(x[pred_genes].sum(1)).ravel() if pred_genes.size else np.zeros(0)
     pred1 = pred_genes[rs > 0]
@@ -568,7 +595,7 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
           pred_genes=None, pred_genes_only=False, null_model=False, mu=None,
           estimates_only=False, *, gene_names=None, cell_names=None, backend=None, comm=None,
           perm=None, fold_seed=0, fold_method="philox", nfolds=5, return_mu=False,
-          verbose=False, gather=True):
+          verbose=False, gather=True, device_prep=True):
     """saver() (R/saver.R:98-179).  x: genes x cells counts (numpy array or scipy.sparse).
 
     pred_cells / pred_genes are 0-based.  ``ncores`` is accepted for signature compatibility;
@@ -608,7 +635,26 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
                              "matrix and no mu; pass x on every rank instead")
         if mu is not None:
             mu = check_mu(x, mu)
-        x, kept = clean_data(x)
+        backend = backend or CudaBackend(comm=comm)
+        # Dense matrices of benchmark size: the whole-matrix passes (threshold, colSums, rowMeans, the
+        # log-normalised design) run on the device from one upload of x; the design never exists on
+        # the host.  clean.data also drops all-zero cells -- if there is one, the host path below runs.
+        ddc = None
+        if (mu is None and not null_model and not hasattr(x, "tocsc") and hasattr(backend, "load_dense")
+                and device_prep and np.ndim(x) == 2 and np.size(x) >= (1 << 20)):
+            xa = np.asarray(x)
+            if xa.shape[1] <= 1:
+                raise SaverError("x should be a matrix with 2 or more columns")
+            if xa.dtype != np.int32:
+                xa = np.ascontiguousarray(xa, dtype=np.float64)
+            ddc = backend.load_dense(np.ascontiguousarray(xa))
+            if (ddc.col_sums == 0).any():
+                ddc.release()
+                ddc = None
+        if ddc is None:
+            x, kept = clean_data(x)
+        else:
+            x, kept = xa, np.ones(xa.shape[1], dtype=bool)
     except SaverError as e:
         if root_only:
             comm.bcast_obj({"error": str(e)})
@@ -619,24 +665,28 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
     if gene_names is None:
         gene_names = np.arange(1, ngenes + 1)
     msg("%d genes, %d cells" % (ngenes, ncells))
-    backend = backend or CudaBackend(comm=comm)
     # sparse input stays sparse on the device; blocks are densified there (csrc/sparse.cu)
     dc = backend.load_counts(x) if hasattr(x, "tocsc") and hasattr(backend, "load_counts") else None
-    sf, scale_sf = calc_size_factor(x if dc is None else _Sums(dc), size_factor, ncells)
+    sums = _Sums(dc) if dc is not None else _Sums(ddc) if ddc is not None else x
+    sf, scale_sf = calc_size_factor(sums, size_factor, ncells)
     if mu is not None:
         out = saver_fit_mean(x, ncores, sf, scale_sf, mu, estimates_only, backend, comm, dc)
     elif null_model and not root_only:
         out = saver_fit_null(x, ncores, sf, scale_sf, estimates_only, backend, comm, dc)
     else:
         pc = get_pred_cells(pred_cells, ncells)
-        pg = get_pred_genes(x if dc is None else _Sums(dc), pred_genes, npred, ngenes)
-        rm = np.asarray(x.mean(1)).ravel() if dc is None else dc.row_sums / ncells
+        pg = get_pred_genes(sums, pred_genes, npred, ngenes)
+        row_sums = None if sums is x else sums.dc.row_sums
+        rm = np.asarray(x.mean(1)).ravel() if row_sums is None else row_sums / ncells
         good = np.where(rm >= 0.1)[0]
         # x.est = t(log((x[good, ] + 1) / sf))  (R/saver.R:156-157), kept gene-major: (p, n)
         if null_model:
             x_est = None
         elif dc is not None:
             x_est = dc.log_rows(good, sf)
+        elif ddc is not None:
+            x_est = ddc.log_rows(good, sf)   # a device panel: goes into set_design / the broadcast as it is
+            ddc.release()
         else:
             x_est = np.log((_dense_rows(x, good) + 1.0) / sf)
         # the x.est column carrying each gene's own name (R/calc_estimate.R:103), -1 if none
@@ -648,6 +698,8 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
                 dc = backend.load_counts(x)
             else:
                 x = x[pg]
+            if row_sums is not None:
+                row_sums = row_sums[pg]
             gene_names = np.asarray(gene_names)[pg]
             self_col = self_col[pg]
             pg = np.arange(x.shape[0])
@@ -659,7 +711,7 @@ def saver(x, do_fast=True, ncores=1, size_factor=None, npred=None, pred_cells=No
                         estimates_only=estimates_only, self_col=self_col, backend=backend,
                         comm=comm, perm=perm, fold_seed=fold_seed, fold_method=fold_method,
                         nfolds=nfolds, keep_mu=return_mu, messages=msg, counts=dc, gather=gather,
-                        root_design=root_only)
+                        root_design=root_only, row_sums=row_sums)
     msg("Done!")
     return _saver_result(out, x, sf, scale_sf, gene_names, cell_names, estimates_only, return_mu,
                          gather)

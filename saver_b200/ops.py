@@ -310,3 +310,50 @@ def csc_gather(gene_idx, sf=None, transform=False, device=False, handle=None):
     h.check(h.lib.saver_cuda_csc_gather(h.h, ptr(idx), B, ptr(sfv), int(bool(transform)), ptr(out),
                                         int(bool(device))))
     return out
+
+
+def set_counts_dense(x, handle=None):
+    """Upload a dense genes x cells count matrix (float64 or int32, C-contiguous) and keep it resident
+    (saver_cuda_set_counts_dense): the whole-matrix passes of saver() then run on the device."""
+    h = handle or default_handle()
+    if not (isinstance(x, np.ndarray) and x.ndim == 2):
+        raise ValueError("x must be a 2-D numpy array")
+    if x.dtype == np.int32:
+        dtype = 1
+    else:
+        x = _f64(x)
+        dtype = 0
+    x = np.ascontiguousarray(x)
+    G, n = x.shape
+    h.check(h.lib.saver_cuda_set_counts_dense(h.h, ptr(x), dtype, G, n))
+    h.dense_shape = (G, n)
+
+
+def dense_sums(handle=None):
+    h = handle or default_handle()
+    G, n = h.dense_shape
+    cs, rs = np.zeros(n), np.zeros(G)
+    h.check(h.lib.saver_cuda_dense_sums(h.h, ptr(cs), ptr(rs)))
+    return cs, rs
+
+
+def dense_gather(gene_idx, sf=None, transform=False, device=False, handle=None):
+    """Dense (B, n) block of the resident dense counts; log((x + 1) / sf) when transform."""
+    h = handle or default_handle()
+    G, n = h.dense_shape
+    idx = np.ascontiguousarray(gene_idx, dtype=np.int32)
+    B = idx.size
+    sfv = None if sf is None else _f64(sf)
+    if device:
+        import torch
+        out = torch.empty((B, n), dtype=torch.float64, device=torch.device("cuda", h.device))
+    else:
+        out = np.empty((B, n))
+    h.check(h.lib.saver_cuda_dense_gather(h.h, ptr(idx), B, ptr(sfv), int(bool(transform)), ptr(out),
+                                          int(bool(device))))
+    return out
+
+
+def release_counts(handle=None):
+    h = handle or default_handle()
+    h.check(h.lib.saver_cuda_release_counts(h.h))

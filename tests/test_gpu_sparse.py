@@ -76,3 +76,42 @@ def test_saver_sparse_with_mu(handle):
     a = saver_b200.saver(x, mu=mu)
     b = saver_b200.saver(sp.csc_matrix(x), mu=mu)
     assert np.array_equal(a.estimate, b.estimate) and np.array_equal(a.se, b.se)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int32])
+def test_dense_device_counts_match_numpy(handle, dtype):
+    """The dense analogue (saver_cuda_set_counts_dense / dense_sums / dense_gather): clean.data's
+    threshold, colSums, rowSums and the log-normalised rows against numpy."""
+    x = _counts(130, 777, 5)
+    if dtype is np.int32:
+        x = np.floor(x)
+    xd = x.astype(dtype)
+    ops.set_counts_dense(xd, handle=handle)
+    xc = np.where(xd < 0.001, 0.0, xd.astype(np.float64))
+    cs, rs = ops.dense_sums(handle=handle)
+    assert np.allclose(cs, xc.sum(0), rtol=1e-14) and np.allclose(rs, xc.sum(1), rtol=1e-14)
+    idx = np.array([129, 3, 5, 0, 17], dtype=np.int32)
+    assert np.array_equal(ops.dense_gather(idx, handle=handle), xc[idx])
+    sf = np.random.default_rng(1).uniform(0.3, 3.0, 777)
+    got = ops.dense_gather(idx, sf=sf, transform=True, device=True, handle=handle).cpu().numpy()
+    assert np.allclose(got, np.log((xc[idx] + 1.0) / sf), rtol=1e-15, atol=1e-15)
+    ops.release_counts(handle=handle)
+    with pytest.raises(saver_b200.SaverCudaError):
+        ops.dense_sums(handle=handle)
+
+
+def test_saver_device_prep_equals_host_prep():
+    """saver() on a matrix large enough for the device preparation path (one upload of x, design
+    built on the device) against the host preparation: the design differs by the device log's last
+    bit at most, the estimates by rounding."""
+    x = synth.nb_counts(1100, 1000, seed=31)
+    x[:, 17] = np.maximum(x[:, 17], 0)  # keep every cell non-empty
+    pg = np.arange(5, 1100, 97)
+    kw = dict(do_fast=False, pred_genes=pg, pred_genes_only=True, fold_seed=4, perm="identity")
+    a = saver_b200.saver(x, device_prep=True, **kw)
+    b = saver_b200.saver(x.astype(np.float64), device_prep=False, **kw)
+    assert np.allclose(a.info["size.factor"], b.info["size.factor"], rtol=1e-14)
+    assert np.array_equal(a.info["lambda.min"] > 0, b.info["lambda.min"] > 0)
+    assert np.allclose(a.info["lambda.max"], b.info["lambda.max"], rtol=1e-9)
+    rel = np.abs(a.estimate - b.estimate) / np.maximum(b.estimate, 1e-12)
+    assert np.median(rel) < 1e-9 and np.quantile(rel, 0.99) < 2e-3   # one ceiling quantum at most
