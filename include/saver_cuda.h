@@ -62,6 +62,14 @@ typedef struct saver_cuda_ctx* saver_cuda_handle;
 SAVER_API int saver_cuda_abi_version(void);
 /* One handle per CUDA device (one process per GPU). */
 SAVER_API int saver_cuda_create(int device, saver_cuda_handle* out);
+/* Several devices behind one handle, for hosts that are ONE process (an R session): the in-process
+ * analogue of the reference's ncores = PSOCK workers (R/saver.R:120-138).  devs[ndev]: CUDA device
+ * ordinals.  On such a handle saver_cuda_set_design installs the design on every device (uploaded
+ * once, then copied device to device) and saver_cuda_calc_estimate splits the block's genes into
+ * contiguous chunks, one per device, on one host thread each (host buffers only); every other entry
+ * point runs on devs[0].  Python hosts use one process per GPU instead (saver_b200/dist.py). */
+SAVER_API int saver_cuda_create_multi(int ndev, const int* devs, saver_cuda_handle* out);
+SAVER_API int saver_cuda_device_count(saver_cuda_handle h);
 SAVER_API int saver_cuda_destroy(saver_cuda_handle h);
 SAVER_API const char* saver_cuda_last_error(saver_cuda_handle h);
 /* Block until all work queued by this handle has finished. */

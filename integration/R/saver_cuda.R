@@ -56,9 +56,25 @@ calc.post <- function(y, mu, sf, scale.sf) {
                rep_len(as.numeric(sf), length(y)), as.numeric(scale.sf))
   list(estimate = out[[1]], se = out[[2]])
 }
-calc.a <- function(y, mu, sf) .Call(C_saver_cuda_calc_var, saver.cuda.handle(), 0L, as.numeric(y), as.numeric(mu), as.numeric(sf))
-calc.b <- function(y, mu, sf) .Call(C_saver_cuda_calc_var, saver.cuda.handle(), 1L, as.numeric(y), as.numeric(mu), as.numeric(sf))
-calc.k <- function(y, mu, sf) .Call(C_saver_cuda_calc_var, saver.cuda.handle(), 2L, as.numeric(y), as.numeric(mu), as.numeric(sf))
+# calc.a / calc.b / calc.k.  Default: the library's deterministic value (the expectation of the
+# reference's Monte-Carlo mean).  options(saver.cuda.r.sample = TRUE) reproduces the reference's own
+# stochastic branch instead (R/optimize_variance.R:46-55,86-95,123-132): the device returns the 100
+# grid points and their log-likelihoods, sample() runs here on R's RNG stream, and the likelihood
+# at the drawn value is one more device evaluation.
+.calc.var <- function(model, loglik.fn, y, mu, sf) {
+  y <- as.numeric(y); mu <- as.numeric(mu); sf <- as.numeric(sf)
+  if (!isTRUE(getOption("saver.cuda.r.sample", FALSE)))
+    return(.Call(C_saver_cuda_calc_var, saver.cuda.handle(), model, y, mu, sf))
+  out <- .Call(C_saver_cuda_calc_var_grid, saver.cuda.handle(), model, y, mu, sf)
+  if (bitwAnd(out[[2]], 1L) == 0L || bitwAnd(out[[2]], 4L) != 0L) return(out[[1]])
+  samp <- out[[3]][1:100]; ll <- out[[3]][101:200]     # ll = log-likelihood = -calc.loglik.*()
+  w <- exp(ll - min(ll)); w <- w / sum(w)
+  p <- mean(sample(samp, 10000, replace = TRUE, prob = w))
+  c(if (model == 2L) p else 1 / p, loglik.fn(p, y, mu, sf))
+}
+calc.a <- function(y, mu, sf) .calc.var(0L, calc.loglik.a, y, mu, sf)
+calc.b <- function(y, mu, sf) .calc.var(1L, calc.loglik.b, y, mu, sf)
+calc.k <- function(y, mu, sf) .calc.var(2L, calc.loglik.k, y, mu, sf)
 calc.loglik.a <- function(a, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.handle(), 0L, a, as.numeric(y), as.numeric(mu), as.numeric(sf))
 calc.loglik.b <- function(b, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.handle(), 1L, b, as.numeric(y), as.numeric(mu), as.numeric(sf))
 calc.loglik.k <- function(k, y, mu, sf) .Call(C_saver_cuda_loglik, saver.cuda.handle(), 2L, k, as.numeric(y), as.numeric(mu), as.numeric(sf))

@@ -134,6 +134,31 @@ SEXP C_saver_cuda_calc_var(SEXP hp, SEXP model, SEXP y, SEXP mu, SEXP sf)
     return out;
 }
 
+/* calc.a / calc.b / calc.k with the 100-point grid of the fallback branch returned as well, so the
+ * R side can do the reference's own draw, mean(sample(samp, 10000, replace = TRUE, prob = .))
+ * (R/optimize_variance.R:46-53), on R's RNG stream: list(c(param, nll), flags, grid[200]).
+ * flags bit 0 = the grid branch was taken; grid = 100 points then their 100 log-likelihoods. */
+SEXP C_saver_cuda_calc_var_grid(SEXP hp, SEXP model, SEXP y, SEXP mu, SEXP sf)
+{
+    saver_cuda_handle h = get_handle(hp);
+    const int n = Rf_length(y);
+    double *py = real_arg(y, n, "y"), *pmu = real_arg(mu, Rf_length(mu) == 1 ? 1 : n, "mu"),
+           *psf = real_arg(sf, Rf_length(sf) == 1 ? 1 : n, "sf");
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP par = PROTECT(Rf_allocVector(REALSXP, 2));
+    SEXP fl = PROTECT(Rf_allocVector(INTSXP, 1));
+    SEXP grid = PROTECT(Rf_allocVector(REALSXP, 200));
+    int flags = 0;
+    check(h, saver_cuda_calc_var(h, Rf_asInteger(model), py, pmu, Rf_length(mu), psf,
+                                 Rf_length(sf), n, REAL(par), &flags, REAL(grid)));
+    INTEGER(fl)[0] = flags;
+    SET_VECTOR_ELT(out, 0, par);
+    SET_VECTOR_ELT(out, 1, fl);
+    SET_VECTOR_ELT(out, 2, grid);
+    UNPROTECT(4);
+    return out;
+}
+
 SEXP C_saver_cuda_loglik(SEXP hp, SEXP model, SEXP param, SEXP y, SEXP mu, SEXP sf)
 {
     saver_cuda_handle h = get_handle(hp);
@@ -269,6 +294,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_saver_cuda_calc_estimate", (DL_FUNC)&C_saver_cuda_calc_estimate, 13},
     {"C_saver_cuda_calc_post", (DL_FUNC)&C_saver_cuda_calc_post, 5},
     {"C_saver_cuda_calc_var", (DL_FUNC)&C_saver_cuda_calc_var, 5},
+    {"C_saver_cuda_calc_var_grid", (DL_FUNC)&C_saver_cuda_calc_var_grid, 5},
     {"C_saver_cuda_loglik", (DL_FUNC)&C_saver_cuda_loglik, 6},
     {"C_saver_cuda_maxcor", (DL_FUNC)&C_saver_cuda_maxcor, 3},
     {"C_saver_cuda_sample", (DL_FUNC)&C_saver_cuda_sample, 6},

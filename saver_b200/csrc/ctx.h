@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/saver_cuda.h"
 #include "saver_kernels.h"
 
@@ -19,6 +21,8 @@ struct saver_cuda_ctx {
   double opt_inner_scale = 1.0;  // saver_cuda_set_option("inner_scale")
   int opt_dbg = 0;  // device time of the variance/posterior and maxcor phases
   char err[512] = {0};
+  // further devices behind this handle (saver_cuda_create_multi); empty for a one-device handle
+  std::vector<saver_cuda_ctx*> peers;
   saver::DesignState design;
   saver::LassoWs lasso;
   // resident sparse counts (sparse.cu)

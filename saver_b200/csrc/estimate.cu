@@ -11,6 +11,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -129,7 +130,7 @@ int build_lambda_seq_host(double lmax, double lmin, double* lg) { return build_l
 double lambda_ratio_host(double flmin, int nlam) { return lambda_ratio(flmin, nlam); }
 }  // namespace saver
 
-extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, int n_cells, int B, const double* sf,
+static int calc_estimate_one(saver_cuda_handle h, const double* X, int n_cells, int B, const double* sf,
                                         double scale_sf, const int* self_col, const int* is_pred,
                                         const int* pred_mask, const int* foldid, int nfolds,
                                         int mode, int calc_maxcor, double cutoff,
@@ -357,6 +358,53 @@ extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, in
   } else {
     memcpy(info6, info.data(), info.size() * 8);
     if (status_out) memcpy(status_out, h_status.data(), B * 4);
+  }
+  return SAVER_OK;
+}
+
+// The public entry point.  A one-device handle runs the block as it is.  A multi handle
+// (saver_cuda_create_multi) splits the block's genes into contiguous chunks, one per device, and runs
+// them on one host thread each -- what calc.estimate does with its row chunks and PSOCK workers
+// (R/calc_estimate.R:69-74,147-160); panels are one gene per column, so a chunk is a pointer offset.
+extern "C" int saver_cuda_calc_estimate(saver_cuda_handle h, const double* X, int n_cells, int B, const double* sf,
+                                        double scale_sf, const int* self_col, const int* is_pred,
+                                        const int* pred_mask, const int* foldid, int nfolds,
+                                        int mode, int calc_maxcor, double cutoff,
+                                        const double* coefs, int dfmax, int nlambda, double thresh,
+                                        double* est, double* se, double* info6, double* mu_out,
+                                        int* status_out, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  const int ndev = 1 + (int)h->peers.size();
+  if (ndev == 1 || B < 2 * ndev)
+    return calc_estimate_one(h, X, n_cells, B, sf, scale_sf, self_col, is_pred, pred_mask, foldid, nfolds, mode,
+                             calc_maxcor, cutoff, coefs, dfmax, nlambda, thresh, est, se, info6, mu_out,
+                             status_out, device_ptrs);
+  if (device_ptrs) return fail(h, SAVER_ERR_ARG, "calc_estimate: a multi-device handle takes host buffers");
+  if (!X || !est || !info6 || n_cells < 2) return fail(h, SAVER_ERR_ARG, "calc_estimate: bad arguments");
+  std::vector<saver_cuda_ctx*> ctx(1, h);
+  ctx.insert(ctx.end(), h->peers.begin(), h->peers.end());
+  std::vector<int> b0(ndev + 1), rc(ndev, SAVER_OK);
+  for (int d = 0; d <= ndev; ++d) b0[d] = (int)((long long)B * d / ndev);
+  std::vector<std::vector<double>> info(ndev);
+  std::vector<std::thread> th;
+  const size_t n = (size_t)n_cells;
+  for (int d = 0; d < ndev; ++d) {
+    const int o = b0[d], nb = b0[d + 1] - b0[d];
+    info[d].assign((size_t)6 * nb, 0.0);
+    th.emplace_back([=, &rc, &info]() {
+      rc[d] = calc_estimate_one(ctx[d], X + n * o, n_cells, nb, sf, scale_sf, self_col ? self_col + o : nullptr,
+                                is_pred ? is_pred + o : nullptr, pred_mask, foldid ? foldid + n * o : nullptr,
+                                nfolds, mode, calc_maxcor, cutoff, coefs, dfmax, nlambda, thresh, est + n * o,
+                                se ? se + n * o : nullptr, info[d].data(), mu_out ? mu_out + n * o : nullptr,
+                                status_out ? status_out + o : nullptr, 0);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < ndev; ++d) {
+    if (rc[d] != SAVER_OK) return fail(h, rc[d], "device %d: %s", ctx[d]->device, ctx[d]->err);
+    const int o = b0[d], nb = b0[d + 1] - b0[d];
+    for (int k = 0; k < 6; ++k)
+      for (int g = 0; g < nb; ++g) info6[(size_t)k * B + o + g] = info[d][(size_t)k * nb + g];
   }
   return SAVER_OK;
 }

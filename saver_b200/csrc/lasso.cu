@@ -1262,8 +1262,12 @@ __device__ __forceinline__ void gram_sweep_g(const double* H, int m, bool by_ind
 
 // The Gram-space round kernel (default): same state machine and phase A as lasso_round_kernel,
 // phase B reformulated so that no coordinate update touches an n-long vector.
-template <int T, bool STAGED>
-__global__ void __launch_bounds__(T, (T <= 128 ? 4 : T <= 256 ? 2 : 1))
+// MINB = resident CTAs per SM the register allocation is planned for.  With two CTAs per SM a thread
+// has 128 registers and ptxas does NOT keep the 12-16 loads of a streaming helper in flight (it
+// interleaves them with their uses: SASS of wdot_a4, profiles/README.md); with one CTA per SM
+// (large n, where W / WR fill shared memory anyway) 255 registers let every batch issue as written.
+template <int T, bool STAGED, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ nextlist,
                    int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -2399,21 +2403,13 @@ cudaError_t launch_round_t(const RoundArgs& A, const int* list, int* nextlist, i
   return launch_round_k<T, false, false>(A, list, nextlist, counter, grid, smem, s);
 }
 
-template <int T>
-cudaError_t launch_gram_t(const RoundArgs& A, const int* list, int* nextlist, int* counter,
-                          int grid, bool staged, size_t smem, cudaStream_t s) {
-  cudaError_t e;
-  if (staged) {
-    e = cudaFuncSetAttribute(lasso_round_gram_kernel<T, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    lasso_round_gram_kernel<T, true><<<grid, T, smem, s>>>(A, list, nextlist, counter);
-  } else {
-    e = cudaFuncSetAttribute(lasso_round_gram_kernel<T, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    lasso_round_gram_kernel<T, false><<<grid, T, smem, s>>>(A, list, nextlist, counter);
-  }
+template <int T, bool STAGED, int MINB>
+cudaError_t launch_gram_k(const RoundArgs& A, const int* list, int* nextlist, int* counter, int grid,
+                          size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(lasso_round_gram_kernel<T, STAGED, MINB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lasso_round_gram_kernel<T, STAGED, MINB><<<grid, T, smem, s>>>(A, list, nextlist, counter);
   return cudaGetLastError();
 }
 
@@ -2540,18 +2536,24 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   bool gram = prm.gram != 0;
   if (tune.gram >= 0) gram = tune.gram != 0;
   int T = ldx <= 2048 ? 128 : ldx <= 4096 ? 256 : ldx <= 8192 ? 512 : 1024;
-  // Gram kernel: 256 threads (two CTAs per SM) while W / WR fit twice; 512 above -- never 1,024: at 64
-  // registers per thread the streaming helpers spill and the kernel runs 25 % slower (profiles/r2_cfg3_cta_size.log)
-  if (gram) T = ldx <= 4096 ? 256 : 512;
+  // Gram kernel: 256 threads and two CTAs per SM (128 registers each) while W / WR fit twice; above
+  // that one CTA per SM of 512 threads.  Alternatives measured at n = 10,000 (profiles/README.md):
+  // 256 threads x 255 registers (the streaming helpers then keep their load batches in flight, but
+  // half the warps: -4 %), 1,024 threads x 64 registers (heavy spills: -20 %), 256 threads unstaged
+  // with two CTAs per SM (-23 %).  SAVER_GRAM_THREADS / SAVER_GRAM_CTAS select them.
+  int minb = ldx <= 4096 ? 2 : 1;
+  if (gram) T = ldx <= 4096 ? 256 : 512;   // measured at n = 10,000: 512 x 128 regs 24.9 genes/s, 256 x 255 regs 23.9
   if (gram && tune.gram_threads > 0) T = tune.gram_threads;
-  if (tune.threads > 0) T = tune.threads;  // tuning experiments only
+  if (gram && T == 512) minb = 1;
+  if (gram && tune.gram_ctas >= 1 && tune.gram_ctas <= 2 && T == 256) minb = tune.gram_ctas;
+  if (!gram && tune.threads > 0) T = tune.threads;  // tuning experiments only
   if (T != 128 && T != 256 && T != 512 && T != 1024) return cudaErrorInvalidValue;
+  if (gram && T != 256 && T != 512) return cudaErrorInvalidValue;
   // Gram kernel shared-memory plan: fixed state, then (staged) W / WR, then the packed Gram block
   // of the warp sweep in whatever is left of the CTA's share of the SM (two CTAs per SM up to 256
   // threads, one above).
   const size_t smem_g0 = kFixedSmem + kGramSmem, smem_gw = (size_t)2 * ldx * 8;
-  int ctas = T <= 128 ? 4 : T <= 256 ? 2 : 1;  // resident CTAs per SM the register cap allows
-  if (tune.gram_ctas >= 1 && tune.gram_ctas < ctas) ctas = tune.gram_ctas;
+  const int ctas = minb;  // resident CTAs per SM the kernel variant is planned for
   size_t budget = (size_t)(228 * 1024 - ctas * 1024) / ctas / 16 * 16;
   if (budget > 227 * 1024) budget = 227 * 1024;
   bool gram_staged = smem_g0 + smem_gw <= budget;
@@ -2621,12 +2623,12 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     A.round_no = rounds;
     if (gram) {
       const size_t sm = smem_gram;
-      switch (T) {
-        case 128: e = launch_gram_t<128>(A, list, next, cnt, live, gram_staged, sm, s); break;
-        case 256: e = launch_gram_t<256>(A, list, next, cnt, live, gram_staged, sm, s); break;
-        case 512: e = launch_gram_t<512>(A, list, next, cnt, live, gram_staged, sm, s); break;
-        default: e = launch_gram_t<1024>(A, list, next, cnt, live, gram_staged, sm, s); break;
-      }
+      if (T == 512) e = gram_staged ? launch_gram_k<512, true, 1>(A, list, next, cnt, live, sm, s)
+                                    : launch_gram_k<512, false, 1>(A, list, next, cnt, live, sm, s);
+      else if (minb == 2) e = gram_staged ? launch_gram_k<256, true, 2>(A, list, next, cnt, live, sm, s)
+                                          : launch_gram_k<256, false, 2>(A, list, next, cnt, live, sm, s);
+      else e = gram_staged ? launch_gram_k<256, true, 1>(A, list, next, cnt, live, sm, s)
+                           : launch_gram_k<256, false, 1>(A, list, next, cnt, live, sm, s);
     } else
     switch (T) {
       case 128: e = launch_round_t<128>(A, list, next, cnt, live, mode, smem, s); break;

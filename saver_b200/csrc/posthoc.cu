@@ -21,70 +21,79 @@ using namespace saver;
 namespace {
 
 // ------------------------------------------------------------------ Philox4x32-10
+// One element (gene, cell, rep) owns the counter stream (idx, rep, block = 0, 1, ...).  Everything is
+// kept in registers: the four words of a block are handed out as a uint4 or through predicated
+// selects (a dynamically indexed array would live in local memory -- 27 % of the kernel's stall
+// samples in the first version, profiles/README.md).
 struct Philox {
-  uint32_t key[2];
-  uint32_t ctr[4];
-  uint32_t out[4];
+  uint32_t k0, k1, c0, c1, c2, c3;
+  uint4 buf;
   int have;
-  __device__ Philox(uint64_t seed, uint64_t idx, uint32_t rep) {
-    key[0] = (uint32_t)seed;
-    key[1] = (uint32_t)(seed >> 32);
-    ctr[0] = (uint32_t)idx;
-    ctr[1] = (uint32_t)(idx >> 32);
-    ctr[2] = rep;
-    ctr[3] = 0;
-    have = 0;
-  }
-  __device__ void round10() {
-    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  __device__ Philox(uint64_t seed, uint64_t idx, uint32_t rep)
+      : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c0((uint32_t)idx), c1((uint32_t)(idx >> 32)),
+        c2(rep), c3(0), have(0) {}
+  __device__ __forceinline__ uint4 block() {
+    uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3, q0 = k0, q1 = k1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-      k0 += 0x9E3779B9u;
-      k1 += 0xBB67AE85u;
+      const uint32_t hi0 = __umulhi(0xD2511F53u, a0), lo0 = 0xD2511F53u * a0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, a2), lo1 = 0xCD9E8D57u * a2;
+      const uint32_t n0 = hi1 ^ a1 ^ q0, n1 = lo1, n2 = hi0 ^ a3 ^ q1, n3 = lo0;
+      a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+      q0 += 0x9E3779B9u;
+      q1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    c3 += 1;  // next block of this element's private stream
+    return make_uint4(a0, a1, a2, a3);
   }
-  __device__ uint32_t next32() {
+  __device__ __forceinline__ uint32_t next32() {
     if (have == 0) {
-      round10();
-      ctr[3] += 1;  // next block of this element's private stream
+      buf = block();
       have = 4;
     }
-    return out[4 - have--];
+    const uint32_t w = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
+    --have;
+    return w;
   }
   // uniform in (0, 1) with 53 random bits
-  __device__ double uniform() {
+  __device__ __forceinline__ double uniform() {
     const uint64_t a = next32(), b = next32();
     const uint64_t v = ((a << 32) | b) >> 11;
     return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
   }
-  __device__ double normal() {  // Box-Muller, one value per call
-    const double u1 = uniform(), u2 = uniform();
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-  }
 };
 
-// Marsaglia-Tsang gamma(shape, 1)
+__device__ __forceinline__ double u32_to_unit(uint32_t w) {  // (0, 1), 32 random bits
+  return ((double)w + 0.5) * (1.0 / 4294967296.0);
+}
+
+// Standard normal from two words: Box-Muller in FP32 (the value is a proposal that is then used in
+// FP64 arithmetic; 32 bits of u1 reach 6.7 sigma, and the result of sample.saver is rounded to three
+// decimals).  The reference draws with R's own generator, so parity here is distributional anyway.
+__device__ __forceinline__ double normal32(uint32_t w0, uint32_t w1) {
+  const float u1 = ((float)w0 + 0.5f) * 2.3283064365386963e-10f;   // (0, 1)
+  const float th = (float)(w1 >> 8) * (6.283185307179586f / 16777216.0f);
+  return (double)(sqrtf(-2.0f * __logf(u1)) * __cosf(th));
+}
+
+// Marsaglia-Tsang gamma(shape, 1): one Philox block per proposal (two words -> the normal, one ->
+// the acceptance uniform, one -> the shape < 1 boost of the first proposal)
 __device__ double gamma_draw(Philox& g, double a) {
   if (!(a > 0.0)) return a == 0.0 ? 0.0 : NAN;
+  const bool small = a < 1.0;
+  const double a1 = small ? a + 1.0 : a;
+  const double d = a1 - 1.0 / 3.0, c = rsqrt(9.0 * d);
   double boost = 1.0;
-  if (a < 1.0) {
-    boost = pow(g.uniform(), 1.0 / a);
-    a += 1.0;
-  }
-  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   for (int it = 0; it < 1000; ++it) {
-    const double x = g.normal();
+    const uint4 w = g.block();
+    if (it == 0 && small) boost = pow(u32_to_unit(w.w), 1.0 / a);
+    const double x = normal32(w.x, w.y);
     double v = 1.0 + c * x;
     if (v <= 0.0) continue;
     v = v * v * v;
-    const double u = g.uniform();
-    if (u < 1.0 - 0.0331 * (x * x) * (x * x) || log(u) < 0.5 * x * x + d * (1.0 - v + log(v)))
-      return boost * d * v;
+    const double u = u32_to_unit(w.z);
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
   }
   return boost * d;
 }

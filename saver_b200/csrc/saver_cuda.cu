@@ -54,8 +54,35 @@ int saver_cuda_create(int device, saver_cuda_handle* out) {
   return SAVER_OK;
 }
 
+// Several devices behind one handle: the in-process analogue of the reference's ncores = PSOCK
+// workers (R/saver.R:120-138) for hosts that are ONE process (an R session).  The first device is
+// the handle itself; the others are ordinary handles kept in `peers`.
+int saver_cuda_create_multi(int ndev, const int* devs, saver_cuda_handle* out) {
+  if (!out) return SAVER_ERR_ARG;
+  *out = nullptr;
+  if (ndev < 1 || !devs) return SAVER_ERR_ARG;
+  saver_cuda_handle h = nullptr;
+  int rc = saver_cuda_create(devs[0], &h);
+  if (rc != SAVER_OK) return rc;
+  for (int i = 1; i < ndev; ++i) {
+    saver_cuda_handle q = nullptr;
+    rc = saver_cuda_create(devs[i], &q);
+    if (rc != SAVER_OK) {
+      saver_cuda_destroy(h);
+      return rc;
+    }
+    h->peers.push_back(q);
+  }
+  *out = h;
+  return SAVER_OK;
+}
+
+int saver_cuda_device_count(saver_cuda_handle h) { return h ? 1 + (int)h->peers.size() : 0; }
+
 int saver_cuda_destroy(saver_cuda_handle h) {
   if (!h) return SAVER_OK;
+  for (saver_cuda_ctx* q : h->peers) saver_cuda_destroy(q);
+  h->peers.clear();
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->design.release();
@@ -71,6 +98,10 @@ const char* saver_cuda_last_error(saver_cuda_handle h) { return h ? h->err : "nu
 
 int saver_cuda_synchronize(saver_cuda_handle h) {
   if (!h) return SAVER_ERR_ARG;
+  for (saver_cuda_ctx* q : h->peers) {
+    const int rc = saver_cuda_synchronize(q);
+    if (rc != SAVER_OK) return fail(h, rc, "%s", q->err);
+  }
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   return SAVER_OK;
@@ -211,6 +242,26 @@ int saver_cuda_set_design(saver_cuda_handle h, const double* xest, int n, int p,
   CU(h->design.build(dX.d, n, p, h->stream));
   h->launches += 1;
   CU(cudaStreamSynchronize(h->stream));
+  // the other devices of a multi handle: the raw design goes device to device (NVLink where the
+  // devices are peers), each device standardises its own copy
+  for (saver_cuda_ctx* q : h->peers) {
+    const size_t bytes = (size_t)n * p * sizeof(double);
+    double* tmp = nullptr;
+    if (cudaSetDevice(q->device) != cudaSuccess || cudaMalloc(&tmp, bytes) != cudaSuccess)
+      return fail(h, SAVER_ERR_NOMEM, "set_design: no memory for the design on device %d", q->device);
+    cudaError_t e = device_ptrs || dX.buf.p
+                        ? cudaMemcpyPeer(tmp, q->device, dX.d, h->device, bytes)
+                        : cudaMemcpy(tmp, xest, bytes, cudaMemcpyHostToDevice);
+    int rc = SAVER_OK;
+    if (e != cudaSuccess) rc = fail(h, SAVER_ERR_CUDA, "set_design: copy to device %d: %s", q->device, cudaGetErrorString(e));
+    else {
+      rc = saver_cuda_set_design(q, tmp, n, p, 1);
+      if (rc != SAVER_OK) fail(h, rc, "%s", q->err);
+    }
+    cudaSetDevice(q->device);
+    cudaFree(tmp);
+    if (rc != SAVER_OK) return rc;
+  }
   return SAVER_OK;
 }
 

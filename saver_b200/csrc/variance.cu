@@ -25,8 +25,11 @@ namespace saver {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kNW = kThreads / 32;
+// CTA size: 256 threads, 512 when a gene has more than 4,096 cells (one CTA per SM there -- the staged
+// columns fill shared memory -- so the extra warps are what hides the FP64 dependency chains of log).
+constexpr int kThreads = 256;      // loglik_kernel and small n
+constexpr int kThreadsBig = 512;
+constexpr int kMaxNW = kThreadsBig / 32;
 constexpr double kBrentTol = 1.220703125e-4;  // .Machine$double.eps^0.25
 
 struct Gene {
@@ -60,8 +63,9 @@ __device__ double loglik(int model, double prm, const Gene& g) {
     // R/calc_loglik.R:34-39
     const double ia = 1.0 / prm;
     double acc[2] = {0.0, 0.0};  // sum [lgamma(y+1/a) - lgamma(1/a)] over y!=0 ; sum (y+1/a) log(sf + 1/(a mu))
-    for (int t = threadIdx.x; t < g.nnz; t += kThreads) acc[0] += lgamma_diff(g.y[g.nz[t]], ia);
-    for (int i = threadIdx.x; i < n; i += kThreads)
+    for (int t = threadIdx.x; t < g.nnz; t += blockDim.x) acc[0] += lgamma_diff(g.y[g.nz[t]], ia);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
       acc[1] += (g.y[i] + ia) * log(g.sf[i] + 1.0 / (prm * g.mu[i]));
     block_sum<2>(acc, g.scratch);
     const double f1 = n / prm * log(ia);
@@ -76,12 +80,13 @@ __device__ double loglik(int model, double prm, const Gene& g) {
     // R/calc_loglik.R:52-56
     const double ib = 1.0 / prm, lib = log(ib);
     double acc[3] = {0.0, 0.0, 0.0};  // sum mu/b log(1/b); sum[lgamma(y+mu/b)-lgamma(mu/b)]; sum (y+mu/b) log(sf+1/b)
-    for (int t = threadIdx.x; t < g.nnz; t += kThreads) {
+    for (int t = threadIdx.x; t < g.nnz; t += blockDim.x) {
       const int i = g.nz[t];
       const double mb = g.mu[i] / prm;
       acc[1] += lgamma_diff(g.y[i], mb);
     }
-    for (int i = threadIdx.x; i < n; i += kThreads) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {  // unrolled: the logs of four cells overlap
       const double mb = g.mu[i] / prm;
       acc[0] += mb * lib;
       acc[2] += (g.y[i] + mb) * log(g.sf[i] + ib);
@@ -92,12 +97,13 @@ __device__ double loglik(int model, double prm, const Gene& g) {
   // R/calc_loglik.R:69-74
   const double lk = log(prm);
   double acc[3] = {0.0, 0.0, 0.0};  // sum mu^2 log(k)/k; lgamma pair; sum (y+mu^2/k) log(sf+mu/k)
-  for (int t = threadIdx.x; t < g.nnz; t += kThreads) {
+  for (int t = threadIdx.x; t < g.nnz; t += blockDim.x) {
     const int i = g.nz[t];
     const double m = g.mu[i], mk = m * m / prm;
     acc[1] += lgamma_diff(g.y[i], mk);
   }
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double m = g.mu[i], m2 = m * m;
     acc[0] += m2 * lk / prm;
     acc[2] += (g.y[i] + m2 / prm) * log(g.sf[i] + m / prm);
@@ -113,10 +119,11 @@ __device__ double loglik(int model, double prm, const Gene& g) {
 // association order (per-lane strided partial sums), i.e. they agree with it to rounding.
 // out[i] = -nll(x_i) for i < 100 (every thread reads them from shared memory afterwards).
 constexpr int kGridPts = 100;
-constexpr int kGridPerWarp = (kGridPts + kNW - 1) / kNW;
+constexpr int kGridPerWarp = (kGridPts + 8 - 1) / 8;  // 8 warps at least
 
 __device__ void loglik_grid(int model, const double* xs, const Gene& g, double* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g.n, kNW = blockDim.x >> 5;
+  const int npw = warp < kGridPts ? (kGridPts - warp + kNW - 1) / kNW : 0;  // grid points of this warp
   double prm[kGridPerWarp], c1[kGridPerWarp], acc[kGridPerWarp];
 #pragma unroll
   for (int q = 0; q < kGridPerWarp; ++q) {
@@ -129,16 +136,18 @@ __device__ void loglik_grid(int model, const double* xs, const Gene& g, double* 
     const int i = g.nz[t];
     const double y = g.y[i], m = g.mu[i];
 #pragma unroll
-    for (int q = 0; q < kGridPerWarp; ++q) {
-      const double al = model == 0 ? c1[q] : model == 1 ? m / prm[q] : m * m / prm[q];
-      acc[q] += lgamma_diff(y, al);
-    }
+    for (int q = 0; q < kGridPerWarp; ++q)
+      if (q < npw) {
+        const double al = model == 0 ? c1[q] : model == 1 ? m / prm[q] : m * m / prm[q];
+        acc[q] += lgamma_diff(y, al);
+      }
   }
   if (model == 0) {
     for (int i = lane; i < n; i += 32) {
       const double y = g.y[i], m = g.mu[i], sfi = g.sf[i];
 #pragma unroll
-      for (int q = 0; q < kGridPerWarp; ++q) acc[q] -= (y + c1[q]) * log(sfi + 1.0 / (prm[q] * m));
+      for (int q = 0; q < kGridPerWarp; ++q)
+        if (q < npw) acc[q] -= (y + c1[q]) * log(sfi + 1.0 / (prm[q] * m));
     }
   } else if (model == 1) {
     double lib[kGridPerWarp];
@@ -147,10 +156,11 @@ __device__ void loglik_grid(int model, const double* xs, const Gene& g, double* 
     for (int i = lane; i < n; i += 32) {
       const double y = g.y[i], m = g.mu[i], sfi = g.sf[i];
 #pragma unroll
-      for (int q = 0; q < kGridPerWarp; ++q) {
-        const double mb = m / prm[q];
-        acc[q] += mb * lib[q] - (y + mb) * log(sfi + c1[q]);
-      }
+      for (int q = 0; q < kGridPerWarp; ++q)
+        if (q < npw) {
+          const double mb = m / prm[q];
+          acc[q] += mb * lib[q] - (y + mb) * log(sfi + c1[q]);
+        }
     }
   } else {
     double lk[kGridPerWarp];
@@ -160,7 +170,7 @@ __device__ void loglik_grid(int model, const double* xs, const Gene& g, double* 
       const double y = g.y[i], m = g.mu[i], sfi = g.sf[i], m2 = m * m;
 #pragma unroll
       for (int q = 0; q < kGridPerWarp; ++q)
-        acc[q] -= m2 * lk[q] / prm[q] + (y + m2 / prm[q]) * log(sfi + m / prm[q]);
+        if (q < npw) acc[q] -= m2 * lk[q] / prm[q] + (y + m2 / prm[q]) * log(sfi + m / prm[q]);
     }
   }
 #pragma unroll
@@ -358,12 +368,12 @@ __device__ FitResult fit_model(int model, double upper, const Gene& g, double* g
 }
 
 template <int STAGE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreadsBig)
 calc_post_kernel(CalcPostArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double scratch[4 * kNW];
+  __shared__ double scratch[4 * kMaxNW];
   __shared__ double grid_s[200];
-  __shared__ int warp_cnt[kNW + 1];
+  __shared__ int warp_cnt[kMaxNW + 1];
 
   const int gi = blockIdx.x;
   const int n = A.n;
@@ -387,7 +397,7 @@ calc_post_kernel(CalcPostArgs A) {
   // ---- stage + first-pass statistics ----
   double st[4] = {0.0, 0.0, 0.0, 0.0};  // sum y, sum y/sf, sum mu, (unused)
   double mu_lo = INFINITY, mu_hi = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double y = gy[i], m = gmu[i], s = A.sf[i];
     if (STAGE == 2) sy[i] = y;
     if (STAGE >= 1) { smu[i] = m; ssf[i] = s; }
@@ -406,7 +416,7 @@ calc_post_kernel(CalcPostArgs A) {
   double* info = A.INFO + (size_t)gi * kPostInfo;
 
   if (st[0] == 0.0) {  // R/calc_posterior.R:34-36
-    for (int i = threadIdx.x; i < n; i += kThreads) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
       est[i] = 0.0;
       if (se) se[i] = 0.0;
     }
@@ -427,7 +437,7 @@ calc_post_kernel(CalcPostArgs A) {
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int base = 0;
-    for (int start = 0; start < n; start += kThreads) {
+    for (int start = 0; start < n; start += blockDim.x) {
       const int i = start + threadIdx.x;
       const bool nzf = (i < n) && (g.y[i] != 0.0);
       const unsigned bal = __ballot_sync(0xffffffffu, nzf);
@@ -436,7 +446,7 @@ calc_post_kernel(CalcPostArgs A) {
       int off = base;
       for (int w = 0; w < warp; ++w) off += warp_cnt[w];
       int tot = 0;
-      for (int w = 0; w < kNW; ++w) tot += warp_cnt[w];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_cnt[w];
       if (nzf) snz[off + __popc(bal & ((1u << lane) - 1))] = i;
       base += tot;
       __syncthreads();
@@ -448,7 +458,7 @@ calc_post_kernel(CalcPostArgs A) {
   // ---- second-pass statistics: var(y/sf), sum log mu, sum mu^2 log mu ----
   const double mean_ysf = st[1] / n;
   double s2[3] = {0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double d = g.y[i] / g.sf[i] - mean_ysf;
     const double m = g.mu[i], lm = log(m);
     s2[0] += d * d;
@@ -499,7 +509,7 @@ calc_post_kernel(CalcPostArgs A) {
   const double scale = 1000.0 * A.scale_sf;
   double* est_raw = A.EST_RAW ? A.EST_RAW + (size_t)gi * n : nullptr;
   double* se_raw = A.SE_RAW ? A.SE_RAW + (size_t)gi * n : nullptr;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double m = g.mu[i];
     double al, be;
     if (method == 0) { al = param; be = param / m; }
@@ -522,7 +532,7 @@ calc_post_kernel(CalcPostArgs A) {
 template <int STAGE>
 __global__ void __launch_bounds__(kThreads) loglik_kernel(LogLikArgs A) {
   // One CTA: calc.loglik.* (mode 0) or calc.a/b/k (mode 1) for a single gene.
-  __shared__ double scratch[4 * kNW];
+  __shared__ double scratch[4 * kMaxNW];
   __shared__ double grid_s[200];
   __shared__ int cnt;
   const int n = A.n;
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(LogLikArgs A) {
   g.nz = A.nz_ws;
   g.nnz = cnt;
   double st[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double m = A.mu[i], lm = log(m);
     st[0] += A.y[i] / A.sf[i];
     st[1] += lm;
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(LogLikArgs A) {
   }
   const double mean_ysf = st[0] / n;
   double ss = 0.0;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double d = A.y[i] / A.sf[i] - mean_ysf;
     ss += d * d;
   }
@@ -589,18 +599,19 @@ cudaError_t launch_calc_post(const CalcPostArgs& A, cudaStream_t stream) {
   int stage;
   const size_t smem = calc_post_smem_bytes(A.n, &stage);
   if (A.B <= 0) return cudaSuccess;
+  const int tpb = A.n > 4096 ? kThreadsBig : kThreads;
   cudaError_t e;
   if (stage == 2) {
     e = cudaFuncSetAttribute(calc_post_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    calc_post_kernel<2><<<A.B, kThreads, smem, stream>>>(A);
+    calc_post_kernel<2><<<A.B, tpb, smem, stream>>>(A);
   } else if (stage == 1) {
     e = cudaFuncSetAttribute(calc_post_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    calc_post_kernel<1><<<A.B, kThreads, smem, stream>>>(A);
+    calc_post_kernel<1><<<A.B, tpb, smem, stream>>>(A);
   } else {
     if (!A.nz_ws) return cudaErrorInvalidValue;
-    calc_post_kernel<0><<<A.B, kThreads, 0, stream>>>(A);
+    calc_post_kernel<0><<<A.B, tpb, 0, stream>>>(A);
   }
   return cudaGetLastError();
 }
