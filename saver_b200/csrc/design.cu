@@ -16,7 +16,8 @@ namespace {
 // one CTA per design column: two-pass mean / sd, write Xs and Xs^2 with zeroed row padding
 __global__ void __launch_bounds__(256)
 standardize_kernel(const double* __restrict__ X, int n, int ldx, double* __restrict__ Xs,
-                   double* __restrict__ Xs2, double* __restrict__ xmean, double* __restrict__ xsd) {
+                   double* __restrict__ Xs2, float* __restrict__ Xf, double* __restrict__ xmean,
+                   double* __restrict__ xsd) {
   __shared__ double scratch[8];
   const int j = blockIdx.x;
   const double* x = X + (size_t)j * n;
@@ -45,10 +46,12 @@ standardize_kernel(const double* __restrict__ X, int n, int ldx, double* __restr
   const double inv = sd > 0.0 ? 1.0 / sd : 0.0;
   double* o = Xs + (size_t)j * ldx;
   double* o2 = Xs2 + (size_t)j * ldx;
+  float* of = Xf + (size_t)j * ldx;
   for (int i = threadIdx.x; i < ldx; i += blockDim.x) {
     const double v = (i < n) ? (x[i] - mean) * inv : 0.0;
     o[i] = v;
     o2[i] = v * v;
+    of[i] = (float)v;
   }
   if (threadIdx.x == 0) {
     xmean[j] = mean;
@@ -116,11 +119,13 @@ cudaError_t DesignState::build(const double* X_dev, int n_, int p_, cudaStream_t
   cudaError_t e;
   if ((e = cudaMalloc(&Xs, bytes)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&Xs2, bytes)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&Xf, bytes / 2)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(Xf, 0, bytes / 2, s)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&xmean, p_pad * sizeof(double))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&xsd, p_pad * sizeof(double))) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(Xs, 0, bytes, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(Xs2, 0, bytes, s)) != cudaSuccess) return e;
-  standardize_kernel<<<p, 256, 0, s>>>(X_dev, n, ldx, Xs, Xs2, xmean, xsd);
+  standardize_kernel<<<p, 256, 0, s>>>(X_dev, n, ldx, Xs, Xs2, Xf, xmean, xsd);
   return cudaGetLastError();
 }
 

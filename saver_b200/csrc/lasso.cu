@@ -30,7 +30,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <type_traits>
+#include <vector>
 
 #include "common.cuh"
 #include "saver_kernels.h"
@@ -47,6 +49,8 @@ void LassoTuning::from_env() {
   geti("SAVER_GRAM_CTAS", gram_ctas);
   geti("SAVER_GRAM_STAGED", gram_staged);
   geti("SAVER_L2_PERSIST", l2_persist);
+  geti("SAVER_LASSO_ORDER", order);
+  geti("SAVER_LASSO_F32", f32);
   if (const char* e = getenv("SAVER_GRAM_HS")) gram_hs = atol(e);
   if (const char* e = getenv("SAVER_STRONG_SLACK")) strong_slack = atof(e);
 }
@@ -70,6 +74,7 @@ constexpr double kVarTiny = 1e-12;  // per-fit variance of a unit-variance colum
 
 struct RoundArgs {
   const double* Xs;
+  const float* Xf;    // FP32 copy of Xs for the Gram model (null: use Xs)
   const double* xsd;
   int n, ldx, p, p_pad, P;
   LassoParams prm;
@@ -390,6 +395,7 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   const double qv = PR->qv, dv0 = PR->dv0, dvr = PR->dvr, shr = PR->shr, ncv = PR->ncv;
   const int n = A.n, ldx = A.ldx, p = A.p, p_pad = A.p_pad;
   const double* __restrict__ Xs = A.Xs;
+  const float* __restrict__ Xf = A.Xf;
   const double* Gc = A.ws.G + (size_t)slot * p_pad;
   const double* XMc = A.ws.XM + (size_t)pid * p_pad;
   const double* XIc = A.ws.XI + (size_t)pid * p_pad;
@@ -982,6 +988,48 @@ __device__ __noinline__ void wdot_wxz4(const double* __restrict__ z0, const doub
   for (int c = 0; c < 4; ++c) out[c] = warp_sum(s0[c] + s1[c]);
 }
 
+__device__ __forceinline__ float4 ldg4f_if(const float* p, bool ok) {
+  return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// wdot_wxz4 on the FP32 copy of the design (curvature model only): four rows per 16-byte load, the
+// products and sums in FP64
+__device__ __noinline__ void wdot_wxz4f(const float* __restrict__ z0, const float* __restrict__ z1,
+                                        const float* __restrict__ z2, const float* __restrict__ z3,
+                                        const float* __restrict__ x, const double* w, int ldx,
+                                        double* out) {
+  const int lane = threadIdx.x & 31;
+  const float* zp[4] = {z0, z1, z2, z3};
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  constexpr int U = 3;
+  for (int i = 4 * lane; i < ldx; i += 128 * U) {
+    float4 zz[4][U], xx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = i + 128 * u < ldx;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zz[c][u] = ldg4f_if(zp[c] + i + 128 * u, ok);
+      xx[u] = ldg4f_if(x + i + 128 * u, ok);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = i + 128 * u < ldx;
+      const double2 wa = lds2_if(w + i + 128 * u, ok), wb = lds2_if(w + i + 128 * u + 2, ok);
+      const double wx0 = wa.x * (double)xx[u].x, wx1 = wa.y * (double)xx[u].y;
+      const double wx2 = wb.x * (double)xx[u].z, wx3 = wb.y * (double)xx[u].w;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        s0[c] += wx0 * (double)zz[c][u].x;
+        s1[c] += wx1 * (double)zz[c][u].y;
+        s0[c] += wx2 * (double)zz[c][u].z;
+        s1[c] += wx3 * (double)zz[c][u].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = warp_sum(s0[c] + s1[c]);
+}
+
 // (pout[c], rout[c]) = (sum_i w_i z_c,i, sum_i r_i z_c,i)
 __device__ __noinline__ void wdot_wr4(const double* __restrict__ z0, const double* __restrict__ z1,
                                       const double* __restrict__ z2, const double* __restrict__ z3,
@@ -1311,6 +1359,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // The list is in completion order of the previous round (quick problems first); taking it from
   // the back starts the long-running problems first, so the round does not end on stragglers.
   const int lpos = (A.prm.dbg & 2048) ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
+  if (list[lpos] < 0) return;  // hole of a gene-aligned list (a fit of the gene that is already done)
   int* INc = A.ws.INACT + (size_t)list[lpos] * A.p_pad;
   const long long t_start = clock64();
   const int pid = list[lpos];
@@ -1324,6 +1373,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   const double shr_in = shr * A.prm.inner_scale;  // exit test of the Gram-space sweeps
   const int n = A.n, ldx = A.ldx, p = A.p, p_pad = A.p_pad;
   const double* __restrict__ Xs = A.Xs;
+  const float* __restrict__ Xf = A.Xf;
   const double* Gc = A.ws.G + (size_t)slot * p_pad;
   const double* XMc = A.ws.XM + (size_t)pid * p_pad;
   const double* XIc = A.ws.XI + (size_t)pid * p_pad;
@@ -1586,10 +1636,35 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       while ((J + 1) * (J + 2) / 2 <= tix) ++J;
       while (J * (J + 1) / 2 > tix) --J;
       const int I = tix - J * (J + 1) / 2;
+      double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+      if (Xf) {  // FP32 copy: 16 rows per step, four k-slices of one 16-byte load per lane
+        auto colf = [&](int idx) { return Xf + (size_t)ia[idx < m ? idx : m - 1] * ldx + 4 * t4; };
+        const float *fI0 = colf(I * 16 + g8), *fI1 = colf(I * 16 + 8 + g8);
+        const float *fJ0 = colf(J * 16 + g8), *fJ1 = colf(J * 16 + 8 + g8);
+#pragma unroll 2
+        for (int base = 0; base < ldx; base += 16) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(fI0 + base));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(fI1 + base));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(fJ0 + base));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(fJ1 + base));
+          const double2 wa = *reinterpret_cast<const double2*>(wv + base + 4 * t4);
+          const double2 wb = *reinterpret_cast<const double2*>(wv + base + 4 * t4 + 2);
+          const double av0[4] = {(double)a0.x, (double)a0.y, (double)a0.z, (double)a0.w};
+          const double av1[4] = {(double)a1.x, (double)a1.y, (double)a1.z, (double)a1.w};
+          const double bv0[4] = {wa.x * (double)b0.x, wa.y * (double)b0.y, wb.x * (double)b0.z, wb.y * (double)b0.w};
+          const double bv1[4] = {wa.x * (double)b1.x, wa.y * (double)b1.y, wb.x * (double)b1.z, wb.y * (double)b1.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dmma(acc[0][0][0], acc[0][0][1], av0[j], bv0[j]);
+            dmma(acc[0][1][0], acc[0][1][1], av0[j], bv1[j]);
+            dmma(acc[1][0][0], acc[1][0][1], av1[j], bv0[j]);
+            dmma(acc[1][1][0], acc[1][1][1], av1[j], bv1[j]);
+          }
+        }
+      } else {
       auto colp = [&](int idx) { return Xs + (size_t)ia[idx < m ? idx : m - 1] * ldx + 2 * t4; };
       const double *cI0 = colp(I * 16 + g8), *cI1 = colp(I * 16 + 8 + g8);
       const double *cJ0 = colp(J * 16 + g8), *cJ1 = colp(J * 16 + 8 + g8);
-      double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
 #pragma unroll 2
       for (int base = 0; base < ldx; base += 8) {
         const double2 a0 = ldg2(cI0 + base), a1 = ldg2(cI1 + base);
@@ -1604,6 +1679,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         dmma(acc[0][1][0], acc[0][1][1], a0.y, b1.y);
         dmma(acc[1][0][0], acc[1][0][1], a1.y, b0.y);
         dmma(acc[1][1][0], acc[1][1][1], a1.y, b1.y);
+      }
       }
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -1832,11 +1908,18 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       };
       if (mlp) {
         for (int lb = 4 * warp; lb < m; lb += 4 * nw) {
+          double acc4[4];
+          if (Xf) {
+            const float* zf[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) zf[c] = Xf + (size_t)ia[lb + c < m ? lb + c : lb] * ldx;
+            wdot_wxz4f(zf[0], zf[1], zf[2], zf[3], Xf + (size_t)k * ldx, wv, ldx, acc4);
+          } else {
           const double* zc[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)ia[lb + c < m ? lb + c : lb] * ldx;
-          double acc4[4];
           wdot_wxz4(zc[0], zc[1], zc[2], zc[3], col, wv, ldx, acc4);
+          }
           if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -2405,12 +2488,69 @@ cudaError_t launch_round_t(const RoundArgs& A, const int* list, int* nextlist, i
 
 template <int T, bool STAGED, int MINB>
 cudaError_t launch_gram_k(const RoundArgs& A, const int* list, int* nextlist, int* counter, int grid,
-                          size_t smem, cudaStream_t s) {
+                          size_t smem, cudaStream_t s, int cluster = 1) {
   cudaError_t e = cudaFuncSetAttribute(lasso_round_gram_kernel<T, STAGED, MINB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if (cluster > 1 && grid % cluster == 0) {
+    // one cluster per gene: the fits of a gene are co-scheduled (same GPC, same instant), nothing else
+    // of the cluster machinery is used
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int* cl = list;
+    return cudaLaunchKernelEx(&cfg, lasso_round_gram_kernel<T, STAGED, MINB>, A, cl, nextlist, counter);
+  }
   lasso_round_gram_kernel<T, STAGED, MINB><<<grid, T, smem, s>>>(A, list, nextlist, counter);
   return cudaGetLastError();
+}
+
+// Gene-adjacent problem list.  `lst` holds the live problems in completion order of the last round;
+// the fits of a gene read the same design columns (their strong / active sets nearly coincide), so
+// they are launched next to each other: the second to sixth reader of a column tile finds it in L2
+// instead of HBM.  Genes keep the order in which their LAST fit finished (the kernel takes the list
+// from the back: long-running genes first).  aligned: every gene gets NF slots, -1 = fit done.
+void order_by_gene(std::vector<int>& lst, int NF, bool aligned) {
+  const int live = (int)lst.size();
+  std::vector<std::pair<int, int>> key(live);  // (gene's last completion position, pid)
+  {
+    std::vector<std::pair<int, int>> bygene(live);
+    for (int i = 0; i < live; ++i) bygene[i] = {lst[i] / NF, i};
+    std::sort(bygene.begin(), bygene.end());
+    for (int a = 0; a < live;) {
+      int b = a;
+      while (b < live && bygene[b].first == bygene[a].first) ++b;
+      const int last = bygene[b - 1].second;  // positions ascend inside a gene
+      for (int i = a; i < b; ++i) key[i] = {last, lst[bygene[i].second]};
+      a = b;
+    }
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int> out;
+  out.reserve(aligned ? (size_t)live * 2 : (size_t)live);
+  for (int a = 0; a < live;) {
+    int b = a;
+    while (b < live && key[b].first == key[a].first) ++b;
+    if (aligned) {
+      const size_t base = out.size();
+      out.resize(base + NF, -1);
+      for (int i = a; i < b; ++i) out[base + key[i].second % NF] = key[i].second;
+    } else {
+      for (int i = a; i < b; ++i) out.push_back(key[i].second);
+    }
+    a = b;
+  }
+  lst.swap(out);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -2488,7 +2628,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     if (!ev && (e = cudaEventCreate(&ev)) != cudaSuccess) return e;
 
   RoundArgs A;
-  A.Xs = D.Xs; A.xsd = D.xsd; A.n = n; A.ldx = ldx; A.p = D.p; A.p_pad = p_pad; A.P = P;
+  A.Xs = D.Xs; A.Xf = ws.tune.f32 == 0 ? nullptr : D.Xf; A.xsd = D.xsd; A.n = n; A.ldx = ldx; A.p = D.p; A.p_pad = p_pad; A.P = P;
   A.prm = prm;
   const LassoTuning& tune = ws.tune;
   if (tune.dbg >= 0) A.prm.dbg = tune.dbg;
@@ -2609,6 +2749,25 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   bool gemm_pending = false;
   int live = ws.h_counter[0];
   int rounds = 0;
+  // problem order of a round: 0 = completion order, 1 = the fits of a gene adjacent, 2 = one
+  // gene-aligned cluster of NF CTAs per gene (gram kernel, 2 <= NF <= 8)
+  int order = gram && NF > 1 ? 1 : 0;
+  if (tune.order >= 0) order = NF > 1 ? tune.order : 0;
+  if (order == 2 && (!gram || NF > 8)) order = 1;
+  std::vector<int> hlist;
+  int grid = live;
+  auto reorder = [&](int* dlist) -> cudaError_t {
+    grid = live;
+    if (order == 0 || live == 0) return cudaSuccess;
+    hlist.resize(live);
+    cudaError_t e2 = cudaMemcpyAsync(hlist.data(), dlist, (size_t)live * 4, cudaMemcpyDeviceToHost, s);
+    if (e2 != cudaSuccess) return e2;
+    if ((e2 = cudaStreamSynchronize(s)) != cudaSuccess) return e2;
+    order_by_gene(hlist, NF, order == 2);
+    grid = (int)hlist.size();
+    return cudaMemcpyAsync(dlist, hlist.data(), (size_t)grid * 4, cudaMemcpyHostToDevice, s);
+  };
+  if ((e = reorder(ws.list0)) != cudaSuccess) return e;
   while (live > 0) {
     if (++rounds > 100000) return cudaErrorUnknown;
     int* list = cur ? ws.list1 : ws.list0;
@@ -2623,12 +2782,13 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
     A.round_no = rounds;
     if (gram) {
       const size_t sm = smem_gram;
-      if (T == 512) e = gram_staged ? launch_gram_k<512, true, 1>(A, list, next, cnt, live, sm, s)
-                                    : launch_gram_k<512, false, 1>(A, list, next, cnt, live, sm, s);
-      else if (minb == 2) e = gram_staged ? launch_gram_k<256, true, 2>(A, list, next, cnt, live, sm, s)
-                                          : launch_gram_k<256, false, 2>(A, list, next, cnt, live, sm, s);
-      else e = gram_staged ? launch_gram_k<256, true, 1>(A, list, next, cnt, live, sm, s)
-                           : launch_gram_k<256, false, 1>(A, list, next, cnt, live, sm, s);
+      const int cl = order == 2 ? NF : 1;
+      if (T == 512) e = gram_staged ? launch_gram_k<512, true, 1>(A, list, next, cnt, grid, sm, s, cl)
+                                    : launch_gram_k<512, false, 1>(A, list, next, cnt, grid, sm, s, cl);
+      else if (minb == 2) e = gram_staged ? launch_gram_k<256, true, 2>(A, list, next, cnt, grid, sm, s, cl)
+                                          : launch_gram_k<256, false, 2>(A, list, next, cnt, grid, sm, s, cl);
+      else e = gram_staged ? launch_gram_k<256, true, 1>(A, list, next, cnt, grid, sm, s, cl)
+                           : launch_gram_k<256, false, 1>(A, list, next, cnt, grid, sm, s, cl);
     } else
     switch (T) {
       case 128: e = launch_round_t<128>(A, list, next, cnt, live, mode, smem, s); break;
@@ -2663,6 +2823,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
       ws.rounds += 1;
     }
     live = ws.h_counter[0];
+    if ((e = reorder(next)) != cudaSuccess) return e;
     cur ^= 1;
     gemm_pending = false;
     if (live > 0) {

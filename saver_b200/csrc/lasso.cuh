@@ -67,6 +67,8 @@ struct LassoTuning {
   long gram_hs = -1;       // SAVER_GRAM_HS: cap (bytes) of the packed Gram block in shared memory
   int l2_persist = -1;     // SAVER_L2_PERSIST: 0 = no persisting-L2 window on the design
   double strong_slack = -1.0;  // SAVER_STRONG_SLACK
+  int f32 = -1;            // SAVER_LASSO_F32: 0 = the curvature model reads the FP64 design too
+  int order = -1;          // SAVER_LASSO_ORDER: 0 completion order, 1 fits of a gene adjacent, 2 + one cluster per gene
   void from_env();
 };
 

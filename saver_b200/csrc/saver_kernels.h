@@ -40,12 +40,14 @@ struct DesignState {
   int p_pad = 0;            // allocated columns: p rounded up to 128
   double* Xs = nullptr;     // ldx x p_pad column-major, (x - mean) / sd_n (1/n variance); constant columns -> 0
   double* Xs2 = nullptr;    // Xs squared elementwise (per-fit second moments come from one GEMM)
+  float* Xf = nullptr;      // Xs rounded to FP32: feeds the lasso's curvature model only (Gram blocks)
   double* xmean = nullptr;  // p
   double* xsd = nullptr;    // p (0 marks a constant column)
   cudaError_t build(const double* X_dev, int n, int p, cudaStream_t s);
   void release() {
-    cudaFree(Xs); cudaFree(Xs2); cudaFree(xmean); cudaFree(xsd);
+    cudaFree(Xs); cudaFree(Xs2); cudaFree(Xf); cudaFree(xmean); cudaFree(xsd);
     Xs = Xs2 = xmean = xsd = nullptr;
+    Xf = nullptr;
     n = p = ldx = p_pad = 0;
   }
 };
