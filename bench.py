@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: genes, cells, seed (seed = 20260 + config#), default gene block per step
-    "cfg3": dict(G=20000, n=10000, seed=20263, block=256),
+    "cfg3": dict(G=20000, n=10000, seed=20263, block=512),
     "cfg2": dict(G=5000, n=2000, seed=20262, block=0),      # 0 = every predictable gene
     "tiny": dict(G=256, n=300, seed=20299, block=0),
     "null": dict(G=20000, n=10000, seed=20263, block=0),

@@ -328,8 +328,9 @@ __global__ void lasso_snapshot_kernel(RoundArgs A) {
 // the round kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kMeta = 64;  // strong-set metadata staged per chunk
+constexpr int kPart = 512;        // doubles: partial sums of the row-split streaming work items
 constexpr int kHSlots = 148 * 4;  // Gram scratch slots (>= resident CTAs of the gram kernel)
-constexpr int kGramSmem = kMeta * 8 + 3 * kNX * 8 + 64 + kNX * 4 - kNX * 8;  // mg, gq, gq2, amat, gsh, ord; as_ lives in global memory
+constexpr int kGramSmem = kMeta * 8 + 3 * kNX * 8 + 64 + kNX * 4 - kNX * 8 + kMeta * 4 + kPart * 8;  // mg, gq, gq2, amat, gsh, ord, mamb, part; as_ lives in global memory
 constexpr int kFixedSmem = 512 * 8 + 6 * kNX * 8 + kNX * 4 + 64 * 4 + kMeta * (8 + 8 + 4 + 4) + 16;
 
 template <int T>
@@ -861,10 +862,10 @@ __device__ __forceinline__ double2 lds2_if(const double* p, bool ok) {
 // sum_i a_i z_i : z a design column (global), a an n-vector (shared or global).  Every lane runs
 // the same number of batches (out-of-range slots load nothing and add an exact zero), so the whole
 // column costs ceil(ldx / (64 kMLP)) exposed L2 round trips.
-__device__ __noinline__ double wdot_a(const double* __restrict__ z, const double* a, int ldx) {
+__device__ __noinline__ double wdot_a(const double* __restrict__ z, const double* a, int r0, int ldx) {
   const int lane = threadIdx.x & 31;
   double s0 = 0.0, s1 = 0.0;
-  for (int i = 2 * lane; i < ldx; i += 64 * kMLP) {
+  for (int i = r0 + 2 * lane; i < ldx; i += 64 * kMLP) {
     double2 zz[kMLP];
 #pragma unroll
     for (int u = 0; u < kMLP; ++u) zz[u] = ldg2_if(z + i + 64 * u, i + 64 * u < ldx);
@@ -996,13 +997,13 @@ __device__ __forceinline__ float4 ldg4f_if(const float* p, bool ok) {
 // products and sums in FP64
 __device__ __noinline__ void wdot_wxz4f(const float* __restrict__ z0, const float* __restrict__ z1,
                                         const float* __restrict__ z2, const float* __restrict__ z3,
-                                        const float* __restrict__ x, const double* w, int ldx,
-                                        double* out) {
+                                        const float* __restrict__ x, const double* w, int r0,
+                                        int ldx, double* out) {
   const int lane = threadIdx.x & 31;
   const float* zp[4] = {z0, z1, z2, z3};
   double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   constexpr int U = 3;
-  for (int i = 4 * lane; i < ldx; i += 128 * U) {
+  for (int i = r0 + 4 * lane; i < ldx; i += 128 * U) {
     float4 zz[4][U], xx[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1030,16 +1031,60 @@ __device__ __noinline__ void wdot_wxz4f(const float* __restrict__ z0, const floa
   for (int c = 0; c < 4; ++c) out[c] = warp_sum(s0[c] + s1[c]);
 }
 
+// Screening dots on the FP32 copy: out[c] = sum_i a_i zf_c,i and outabs[c] = sum_i |a_i zf_c,i|.
+// Every FP32 entry is its FP64 original times (1 + e), |e| <= 2^-24, so the exact dot lies within
+// 2^-24 * outabs[c] of out[c]: candidates that this interval separates from the threshold need no
+// FP64 pass (the strong-set check), the others are recomputed exactly.
+__device__ __noinline__ void wdot_a4f(const float* __restrict__ z0, const float* __restrict__ z1,
+                                      const float* __restrict__ z2, const float* __restrict__ z3,
+                                      const double* a, int r0, int ldx, double* out,
+                                      double* outabs) {
+  const int lane = threadIdx.x & 31;
+  const float* zp[4] = {z0, z1, z2, z3};
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0};
+  constexpr int U = 3;
+  for (int i = r0 + 4 * lane; i < ldx; i += 128 * U) {
+    float4 zz[4][U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zz[c][u] = ldg4f_if(zp[c] + i + 128 * u, i + 128 * u < ldx);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = i + 128 * u < ldx;
+      const double2 ra = lds2_if(a + i + 128 * u, ok), rb = lds2_if(a + i + 128 * u + 2, ok);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double p0 = ra.x * (double)zz[c][u].x, p1 = ra.y * (double)zz[c][u].y;
+        const double p2 = rb.x * (double)zz[c][u].z, p3 = rb.y * (double)zz[c][u].w;
+        s0[c] += p0;
+        s1[c] += p1;
+        s0[c] += p2;
+        s1[c] += p3;
+        t0[c] += fabs(p0);
+        t1[c] += fabs(p1);
+        t0[c] += fabs(p2);
+        t1[c] += fabs(p3);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    out[c] = warp_sum(s0[c] + s1[c]);
+    outabs[c] = warp_sum(t0[c] + t1[c]);
+  }
+}
+
 // (pout[c], rout[c]) = (sum_i w_i z_c,i, sum_i r_i z_c,i)
 __device__ __noinline__ void wdot_wr4(const double* __restrict__ z0, const double* __restrict__ z1,
                                       const double* __restrict__ z2, const double* __restrict__ z3,
-                                      const double* w, const double* r, int ldx, double* pout,
-                                      double* rout) {
+                                      const double* w, const double* r, int r0, int ldx,
+                                      double* pout, double* rout) {
   const int lane = threadIdx.x & 31;
   const double* zp[4] = {z0, z1, z2, z3};
   double pa[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0}, ra[4] = {0, 0, 0, 0}, rb[4] = {0, 0, 0, 0};
   constexpr int U = 3;
-  for (int i = 2 * lane; i < ldx; i += 64 * U) {
+  for (int i = r0 + 2 * lane; i < ldx; i += 64 * U) {
     double2 zz[4][U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -1337,7 +1382,9 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   double* amat = gq2 + kNX;                                // coefficients at the last materialisation
   double* gsh = amat + kNX;                                // 8 doubles: sweep results broadcast from warp 0
   int* ord = reinterpret_cast<int*>(gsh + 8);              // active positions by variable index
-  double* wv = reinterpret_cast<double*>(ord + kNX);
+  int* mamb = ord + kNX;                                   // FP32 screening: candidates that need the FP64 dot
+  double* part = reinterpret_cast<double*>(mamb + kMeta);  // partial dots of (column group, row segment) items
+  double* wv = part + kPart;
   double* wrv = wv + A.ldx;
   double* Hsm = STAGED ? wrv + A.ldx : wv;                 // packed Gram block (A.mh rows at most)
   const int mh = A.mh;
@@ -1580,26 +1627,67 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   bool H_fresh = false;  // ... and it was built with the current working weights
   bool dirty = false;
 
+  // A streaming phase over ng groups of 4 columns costs one column pass per round of T/32 groups,
+  // however few groups there are (a single warp cannot pull more than ~2 GB/s; the SM reaches its
+  // share of HBM only with every warp streaming: profiles/r2_ubench_stream.log).  Short phases are
+  // therefore cut into (group, row segment) items: S segments per column, chosen to minimise
+  // rounds x segment length, partial sums combined through `part`.
+  auto pick_split = [&](int ng, int maxitems) -> int {
+    if (A.prm.dbg & 65536) return 1;
+    const int nw = T >> 5;
+    int best = 1, bc = (ng + nw - 1) / nw * 16;
+    for (int s2 = 2; s2 <= 16; s2 *= 2) {
+      if (ng * s2 > maxitems || s2 * 512 > ldx) break;
+      const int c = (ng * s2 + nw - 1) / nw * (16 / s2);
+      if (c < bc) { bc = c; best = s2; }
+    }
+    return best;
+  };
+  auto seg_len = [&](int S) { return ((ldx + S - 1) / S + 127) & ~127; };
   // p_l = sum w Xs_l -> swa[l], r_l = sum wr Xs_l -> gq[l]   (four columns per reduction)
-  // (one warp per column, independent accumulators per lane, no block barrier inside)
+  // (one warp per column group / row segment, independent accumulators per lane)
   auto gram_vectors = [&](int l0, int l1, bool with_p) {
     crumb_m = l1;
     crumb(17);
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
     if (mlp) {
-      for (int lb = l0 + 4 * warp; lb < l1; lb += 4 * nw) {
+      const int ng = (l1 - l0 + 3) >> 2, S = pick_split(ng, kPart / 8), sl = seg_len(S);
+      for (int item = warp; item < ng * S; item += nw) {
+        const int grp = item / S, seg = item - grp * S, lb = l0 + 4 * grp;
+        const int r0 = seg * sl, r1 = r0 + sl < ldx ? r0 + sl : ldx;
         const double* zc[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)ia[lb + c < l1 ? lb + c : lb] * ldx;
         double ps4[4], rs4[4];
-        wdot_wr4(zc[0], zc[1], zc[2], zc[3], wv, wrv, ldx, ps4, rs4);
+        wdot_wr4(zc[0], zc[1], zc[2], zc[3], wv, wrv, r0, r1, ps4, rs4);
         if (lane == 0) {
+          if (S == 1) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (lb + c < l1) {
-              if (with_p) swa[lb + c] = ps4[c];
-              gq[lb + c] = rs4[c];
+            for (int c = 0; c < 4; ++c)
+              if (lb + c < l1) {
+                if (with_p) swa[lb + c] = ps4[c];
+                gq[lb + c] = rs4[c];
+              }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              part[item * 8 + c] = ps4[c];
+              part[item * 8 + 4 + c] = rs4[c];
             }
+          }
+        }
+      }
+      if (S > 1) {
+        __syncthreads();
+        for (int l = l0 + tid; l < l1; l += T) {
+          const int grp = (l - l0) >> 2, c = (l - l0) & 3;
+          double ps = 0.0, rs = 0.0;
+          for (int seg = 0; seg < S; ++seg) {
+            ps += part[(grp * S + seg) * 8 + c];
+            rs += part[(grp * S + seg) * 8 + 4 + c];
+          }
+          if (with_p) swa[l] = ps;
+          gq[l] = rs;
         }
       }
     } else
@@ -1906,15 +1994,39 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         if (grow) hrow[l] = h;
         gq[l] -= d * h;
       };
-      if (mlp) {
+      if (mlp && Xf) {
+        const int ng = (m + 3) >> 2, S = pick_split(ng, kPart / 4), sl = seg_len(S);
+        for (int item = warp; item < ng * S; item += nw) {
+          const int grp = item / S, seg = item - grp * S, lb = 4 * grp;
+          const int r0 = seg * sl, r1 = r0 + sl < ldx ? r0 + sl : ldx;
+          const float* zf[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) zf[c] = Xf + (size_t)ia[lb + c < m ? lb + c : lb] * ldx;
+          double acc4[4];
+          wdot_wxz4f(zf[0], zf[1], zf[2], zf[3], Xf + (size_t)k * ldx, wv, r0, r1, acc4);
+          if (lane == 0) {
+            if (S == 1) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (lb + c < m) put(lb + c, acc4[c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) part[item * 4 + c] = acc4[c];
+            }
+          }
+        }
+        if (S > 1) {
+          __syncthreads();
+          for (int l = tid; l < m; l += T) {
+            double acc = 0.0;
+            for (int seg = 0; seg < S; ++seg) acc += part[((l >> 2) * S + seg) * 4 + (l & 3)];
+            put(l, acc);
+          }
+        }
+      } else if (mlp) {
         for (int lb = 4 * warp; lb < m; lb += 4 * nw) {
           double acc4[4];
-          if (Xf) {
-            const float* zf[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) zf[c] = Xf + (size_t)ia[lb + c < m ? lb + c : lb] * ldx;
-            wdot_wxz4f(zf[0], zf[1], zf[2], zf[3], Xf + (size_t)k * ldx, wv, ldx, acc4);
-          } else {
+          {
           const double* zc[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)ia[lb + c < m ? lb + c : lb] * ldx;
@@ -1972,6 +2084,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
   // Strong-set check of the inactive variables (KKT inside the strong set): g_k = x~_k^T wr for a
   // staged chunk of candidates, one warp per column; the first variable (in index order) whose
   // |g_k| exceeds lambda enters, after which the rest of the chunk is evaluated again.
+  const bool screen = Xf != nullptr && !(A.prm.dbg & 32768);  // bit 32768: FP64 strong-set dots only
   auto inactive_check = [&](int& m, double& dlx, bool& overflow) {
     if (ninact == 0) return;
     tph[11] += 1;
@@ -1994,7 +2107,74 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       crumb_m = cur;
       crumb(15);
       while (j0 < cn) {
-        if (mlp) {
+        if (mlp && screen) {
+          // screen on the FP32 copy: |g| is decided against lambda by an interval that contains the
+          // FP64 value; the undecided and the violators get the FP64 dot below
+          const int ng = (cn - j0 + 3) >> 2, S = pick_split(ng, kPart / 8), sl = seg_len(S);
+          for (int item = warp; item < ng * S; item += nw) {
+            const int grp = item / S, seg = item - grp * S, jb = j0 + 4 * grp;
+            const int r0 = seg * sl, r1 = r0 + sl < ldx ? r0 + sl : ldx;
+            bool need[4], any = false;
+            int first = -1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              need[c] = jb + c < cn && mpos[jb + c] < 0;
+              any |= need[c];
+              if (need[c] && first < 0) first = jb + c;
+            }
+            if (!any) continue;
+            const float* zf[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) zf[c] = Xf + (size_t)mk[need[c] ? jb + c : first] * ldx;
+            double acc4[4], abs4[4];
+            wdot_a4f(zf[0], zf[1], zf[2], zf[3], wrv, r0, r1, acc4, abs4);
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                part[item * 8 + c] = acc4[c];
+                part[item * 8 + 4 + c] = abs4[c];
+              }
+            }
+          }
+          __syncthreads();
+          for (int j = j0 + tid; j < cn; j += T)
+            if (mpos[j] < 0) {
+              const int grp = (j - j0) >> 2, c = (j - j0) & 3;
+              double acc = 0.0, ab = 0.0;
+              for (int seg = 0; seg < S; ++seg) {
+                acc += part[(grp * S + seg) * 8 + c];
+                ab += part[(grp * S + seg) * 8 + 4 + c];
+              }
+              const double gf = mxi[j] * (acc - mxm[j] * q0);
+              const double bnd = mxi[j] * ab * 6.0e-8 + fabs(gf) * 1e-13;
+              mg[j] = gf;
+              mamb[j] = !(fabs(gf) + bnd <= al);
+            }
+          __syncthreads();
+          // FP64 dots of the flagged candidates, every warp on its row segment of one column
+          int S2 = 1;
+          while (S2 < nw && 2 * S2 * 512 <= ldx) S2 *= 2;
+          const int sl2 = seg_len(S2);
+          for (int j = j0; j < cn; ++j)
+            if (mpos[j] < 0 && mamb[j]) {
+              if (warp < S2) {
+                const int r0 = warp * sl2, r1 = r0 + sl2 < ldx ? r0 + sl2 : ldx;
+                const double acc = wdot_a(Xs + (size_t)mk[j] * ldx, wrv, r0, r1);
+                if (lane == 0) part[warp] = acc;
+              }
+              __syncthreads();
+              if (tid == 0) {
+                double acc = 0.0;
+                for (int seg = 0; seg < S2; ++seg) acc += part[seg];
+                mg[j] = mxi[j] * (acc - mxm[j] * q0);
+              }
+              tph[15] += 1;
+              __syncthreads();
+              // the scan below stops at the first violator in index order: later candidates are
+              // evaluated again after it has entered, their FP64 value is not needed now
+              if (fabs(mg[j]) > al) break;
+            }
+        } else if (mlp) {
           for (int jb = j0 + 4 * warp; jb < cn; jb += 4 * nw) {
             const double* zc[4];
             bool need[4], any = false;
@@ -2006,9 +2186,9 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
               if (need[c] && first < 0) first = jb + c;
             }
             if (!any) continue;
+            double acc4[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) zc[c] = Xs + (size_t)mk[need[c] ? jb + c : first] * ldx;
-            double acc4[4];
             wdot_a4(zc[0], zc[1], zc[2], zc[3], wrv, ldx, acc4);
             if (lane == 0) {
 #pragma unroll

@@ -67,9 +67,9 @@ def main():
             names = ["phaseA", "vectors", "gramP", "sweeps", "material", "inactive", "relin"]
             tot = ph[:7].sum() + ph[13]
             print("   phases: " + " ".join("%s %.1f%%" % (k, 100 * q / tot) for k, q in zip(names, ph[:7]))
-                  + " activate %.1f%% | IRLS/gene %.0f mean m %.0f inactive cols/IRLS %.0f act/IRLS %.2f" % (
+                  + " activate %.1f%% | IRLS/gene %.0f mean m %.0f inactive cols/IRLS %.0f act/IRLS %.2f fp64 rechecks/IRLS %.2f" % (
                       100 * ph[13] / tot, ph[7] / G, ph[12] / max(ph[7], 1), ph[10] / max(ph[7], 1),
-                      ph[14] / max(ph[7], 1)), flush=True)
+                      ph[14] / max(ph[7], 1), ph[15] / max(ph[7], 1)), flush=True)
         h.close()
         del h
 

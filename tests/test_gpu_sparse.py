@@ -63,8 +63,13 @@ def test_saver_sparse_equals_dense(kw):
     a = saver_b200.saver(x, fold_seed=5, **kw)
     b = saver_b200.saver(sp.csr_matrix(x), fold_seed=5, **kw)
     # the counts panels are identical; the design differs by the ulp between the device's log and
-    # numpy's, which the 3-decimal rounding of the prediction absorbs (R/expr_predict.R:58,80)
-    assert np.allclose(a.estimate, b.estimate, rtol=1e-9) and np.allclose(a.se, b.se, rtol=1e-9)
+    # numpy's, which the 3-decimal rounding of the prediction absorbs (R/expr_predict.R:58,80).  The
+    # solver's curvature model reads an FP32 copy of the design, where that ulp can become an FP32
+    # ulp: the iterates then agree to ~1e-8 instead of 1e-15, which can move a value across one
+    # step of the 3-decimal ceiling of estimate / se (R/calc_posterior.R:66-67) in a few cells.
+    for u, v in ((a.estimate, b.estimate), (a.se, b.se)):
+        d = np.abs(u - v)
+        assert d.max() <= 1.0001e-3 and (d > 1e-9).mean() < 1e-3
     assert np.array_equal(a.info["size.factor"], b.info["size.factor"])
     for k in ("maxcor", "lambda.max", "lambda.min", "sd.cv"):
         assert np.allclose(a.info[k], b.info[k], rtol=1e-9, equal_nan=True), k
