@@ -238,18 +238,19 @@ def run_fast(args):
 def run_cfg5(args):
     import bench
     import saver_b200
-    from saver_b200 import ops
+    from saver_b200 import host, ops
     torch, rank, world, local, dev, comm = _env()
     h = saver_b200.Handle(local)
     stream = torch.cuda.ExternalStream(h.stream(), device=dev)
     G, n = (20000, 10000) if args.block is None else (args.block, 10000)
-    # est / se of the shape saver() returns at cfg3 (posterior mean / sd of a Gamma): synthetic
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(20265)
+    # est / se of the shape saver() returns at cfg3 (posterior mean / sd of a Gamma): synthetic; every
+    # rank holds only ITS genes (the layout saver(comm=, gather=False) leaves behind)
     e = [(G * r) // world for r in range(world + 1)]
     g0, g1 = e[rank], e[rank + 1]
-    est_all = (torch.rand((G, n), generator=gen, device=dev, dtype=torch.float64) * 3.0 + 0.05)
-    se_all = est_all * (0.2 + 0.5 * torch.rand((G, n), generator=gen, device=dev, dtype=torch.float64))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20265 + rank)
+    est = torch.rand((g1 - g0, n), generator=gen, device=dev, dtype=torch.float64) * 3.0 + 0.05
+    se = est * (0.2 + 0.5 * torch.rand((g1 - g0, n), generator=gen, device=dev, dtype=torch.float64))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = torch.empty((g1 - g0, n), dtype=torch.float64, device=dev)
 
@@ -262,10 +263,10 @@ def run_cfg5(args):
     def samp(nb):
         def f():
             blk = 4096
-            for b0 in range(g0, g1, blk):
-                b1 = min(b0 + blk, g1)
-                out[b0 - g0:b1 - g0] = ops.sample(est_all[b0:b1], se_all[b0:b1], nb_mode=nb, seed=50,
-                                                 rep_idx=0, gene0=b0, handle=h)
+            for b0 in range(0, g1 - g0, blk):
+                b1 = min(b0 + blk, g1 - g0)
+                out[b0:b1] = ops.sample(est[b0:b1], se[b0:b1], nb_mode=nb, seed=50, rep_idx=0,
+                                        gene0=g0 + b0, handle=h)
         return f
 
     clocks = bench.ClockSampler(local)
@@ -273,42 +274,83 @@ def run_cfg5(args):
     clocks.start()
     t_gamma = _timed(samp(False), args.steps, args.warmup, stream, flush, torch, barrier)
     t_nb = _timed(samp(True), args.steps, args.warmup, stream, flush, torch, barrier)
-    # cor.genes: this rank's column panel of the symmetric G x G matrix
     del out
-    cor = [None]
+    # cor.genes.  N = 1: the upper-triangle blocks of an 8 x 8 blocking, mirrored.  N > 1: all-gather of
+    # the standardised rows (NCCL), every rank fills its G/N x G row panel, of which only the blocks of
+    # its cyclic window are computed (the others are transposes of blocks other ranks own).
+    res = {}
 
-    def corf():
-        cor[0] = None
-        cor[0] = ops.cor_adjust(est_all, se_all, by_cells=False, col0=g0, ncols=g1 - g0, handle=h)
+    def cor_one():
+        nblk = 8
+        Z, adj = ops.cor_prep(est, se, handle=h)
+        Zp = torch.cat([Z, torch.zeros((128, Z.shape[1]), dtype=Z.dtype, device=dev)], 0)
+        del Z
+        full = torch.empty((G, G), dtype=torch.float64, device=dev)
+        ed = [(G * b) // nblk for b in range(nblk + 1)]
+        torch.cuda.synchronize()
+        for i in range(nblk):
+            for j in range(i, nblk):
+                ops.cor_block(Zp, adj, G, ed[j], ed[j + 1] - ed[j], ed[i], ed[i + 1] - ed[i],
+                              full[ed[i]:ed[i + 1]], handle=h)
+        h.synchronize()
+        for i in range(nblk):
+            for j in range(i + 1, nblk):
+                full[ed[j]:ed[j + 1], ed[i]:ed[i + 1]] = full[ed[i]:ed[i + 1], ed[j]:ed[j + 1]].T
+        torch.cuda.synchronize()
+        res["panel"], res["blocks"], res["flops"] = full, nblk * (nblk + 1) // 2, None
 
-    t_cor = _timed(corf, max(1, args.steps // 2), 1, stream, flush, torch, barrier)
+    def cor_many():
+        res.pop("panel", None)
+        panel, (c0, c1), blocks = host.cor_genes_sharded(est, se, comm, handle=h)
+        res["panel"], res["blocks"] = panel, len(blocks)
+
+    csteps = max(1, args.steps // 2)
+    gathered0 = comm.bytes_gathered if comm is not None else 0
+    t0 = None
+    corf = cor_one if comm is None else cor_many
+    corf()
+    barrier()
+    t0 = time.time()
+    for _ in range(csteps):
+        corf()
+    barrier()
+    t_cor = time.time() - t0
     clk = clocks.stop()
     launches = h.launch_count() - l0
-    csteps = max(1, args.steps // 2)
+    gathered = ((comm.bytes_gathered - gathered0) // (csteps + 1)) if comm is not None else 0
     tg, tn, tc = _max_over_ranks(comm, [t_gamma, t_nb, t_cor], dev, torch)
     if rank == 0:
         hbm, which = bench.peaks()
-        d = np.diag(cor[0][:, g0:g1].cpu().numpy()) if g1 - g0 <= 4096 else None
+        pan = res["panel"]
+        d = torch.diagonal(pan[:, g0:g1]).cpu().numpy()
         sb = 24.0 * n * G
+        useful = 1.0 * G * G * n        # 2 n flop per entry of the upper triangle
         line = {
             "metric": "genes/sec, sample.saver (gamma) on saver() output, 20k x 10k",
             "value": G * args.steps / tg, "unit": "genes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tg * 1e3 / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg5: sample.saver(rep = 1, seed = 50) gamma and NB modes + cor.genes on "
-                                   "est / se of %d genes x %d cells" % (G, n),
+                                   "est / se of %d genes x %d cells, genes in contiguous blocks over the "
+                                   "ranks" % (G, n),
                        "l2": "flushed between steps (256 MiB write)"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": None,
             "roofline": {"kernel": "sample_kernel (gamma mode)", "bound": "hbm", "unit": "GB/s",
-                         "achieved": sb * args.steps / tg / 1e9, "peak": hbm, "frac": sb * args.steps / tg / 1e9 / hbm,
+                         "achieved": sb * args.steps / tg / 1e9, "peak": hbm * world,
+                         "frac": sb * args.steps / tg / 1e9 / (hbm * world),
                          "peak_source": which, "traffic": None, "algorithmic": "24*n B/gene/rep"},
             "sample_nb": {"genes_per_s": G * args.steps / tn, "GBps": sb * args.steps / tn / 1e9,
-                          "frac_hbm": sb * args.steps / tn / 1e9 / hbm},
-            "cor_genes": {"s_per_call": tc / csteps, "tflops": 2.0 * G * G * n * csteps / tc / 1e12,
-                          "flops": "2*G^2*n (each rank: a G x G/N column panel, inputs replicated)",
-                          "out_bytes": int(G) * G * 8,
-                          "diag_is_adj2_le_1": None if d is None else bool((d <= 1.0 + 1e-12).all())},
+                          "frac_hbm": sb * args.steps / tn / 1e9 / (hbm * world)},
+            "cor_genes": {"s_per_call": tc / csteps,
+                          "useful_tflops": useful * csteps / tc / 1e12,
+                          "flops": "G^2 n (2 n per entry of the upper triangle; the blocks computed cover it "
+                                   "plus half of the diagonal blocks); wall time of the whole call incl. "
+                                   "standardisation, all-gather%s" % ("" if comm is not None else ", mirror copy"),
+                          "blocks_on_rank0": res["blocks"],
+                          "allgather_bytes": int(gathered),
+                          "out_bytes_per_rank": int(pan.numel()) * 8,
+                          "diag_is_adj2_le_1": bool((d <= 1.0 + 1e-12).all() and (d > 0).all())},
         }
         print(json.dumps(line), flush=True)
     _finish(comm)

@@ -182,6 +182,20 @@ SAVER_API int saver_cuda_cor_adjust(saver_cuda_handle h, const double* est, cons
                                     int G, int by_cells, const double* cor_in, int col0, int ncols,
                                     double* out, int device_ptrs);
 
+/* ---- cor.genes with the genes spread over ranks (R/cor_adjust.R:32-42 on a gene-sharded saver object) ----
+ * saver_cuda_cor_prep: est, se n x B (this rank's genes) -> Z (ldz x B, ldz = n rounded up to 16,
+ * rows beyond n zeroed): centred unit-norm rows, so that Z^T Z = cor(t(est)); adj (B) =
+ * sqrt(var / (var + mean(se^2))).  The ranks exchange Z / adj (one all-gather), then
+ * saver_cuda_cor_block writes out[row0 .. row0+nrows, c] (column-major, leading dimension ldo, c
+ * counted from col0) = clamp(Z_r . Z_c) * adj_r * adj_c for one rectangular block, from the
+ * gathered panel (device pointers; Z allocated and zeroed up to round_up(M, 128) + 64 columns).
+ * The matrix is symmetric: a rank needs only the blocks on or above its place in a cyclic order. */
+SAVER_API int saver_cuda_cor_prep(saver_cuda_handle h, const double* est, const double* se, int n,
+                                  int B, double* Z, int ldz, double* adj, int device_ptrs);
+SAVER_API int saver_cuda_cor_block(saver_cuda_handle h, const double* Z, int ldz, const double* adj,
+                                   int M, int row0, int nrows, int col0, int ncols, double* out,
+                                   int ldo);
+
 /* ---- sparse counts: R's dgCMatrix (genes x cells, compressed by cell: slots p, i, x) ----
  * Uploaded once and kept resident.  Values < 0.001 are zeroed on upload (clean.data,
  * R/utils.R:11-19).  Host pointers. */

@@ -181,9 +181,10 @@ cor_prep_kernel(const double* __restrict__ E, const double* __restrict__ S, int 
   if (threadIdx.x == 0) adj[v] = sqrt(var / (var + mse));
 }
 
-__global__ void cor_scale_kernel(double* __restrict__ C, int ldc, int M, int ncols, int col0,
-                                 const double* __restrict__ adj, const double* __restrict__ cor_in,
-                                 int ld_in) {
+// C (M rows x ncols, ld = ldc) *= outer(adj_r, adj_c); C, adj_r, adj_c already point at the block
+__global__ void cor_scale_kernel(double* __restrict__ C, int ldc, int M, int ncols,
+                                 const double* __restrict__ adj_r, const double* __restrict__ adj_c,
+                                 const double* __restrict__ cor_in, int ld_in) {
   const size_t tot = (size_t)M * ncols;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -191,7 +192,7 @@ __global__ void cor_scale_kernel(double* __restrict__ C, int ldc, int M, int nco
     const size_t o = (size_t)c * ldc + r;
     double v = cor_in ? cor_in[(size_t)c * ld_in + r] : C[o];
     if (!cor_in && v == v) v = fmin(1.0, fmax(-1.0, v));  // stats::cor clamps to [-1, 1]; NA stays NA
-    C[o] = v * adj[r] * adj[col0 + c];
+    C[o] = v * adj_r[r] * adj_c[c];
   }
 }
 
@@ -285,10 +286,58 @@ extern "C" int saver_cuda_cor_adjust(saver_cuda_handle h, const double* est, con
     CU(launch_gemm_tn_f64(Z.p, ldk, Z.p + (size_t)ldk * col0, ldk, dO.d, M, M, ncols, ldk, s));
     h->launches += 1;
   }
-  cor_scale_kernel<<<kGrid, 256, 0, s>>>(dO.d, M, M, ncols, col0, adj.p, dC.d, M);
+  cor_scale_kernel<<<kGrid, 256, 0, s>>>(dO.d, M, M, ncols, adj.p, adj.p + col0, dC.d, M);
   CU(cudaGetLastError());
   h->launches += 1;
   CU(dO.fetch(s));
   if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}
+
+// ---- cor.genes over ranks: the two halves of saver_cuda_cor_adjust as separate calls ----
+// saver_cuda_cor_prep standardises this rank's B genes (unit-norm centred rows, so Z^T Z = cor) and
+// computes their adj; the ranks all-gather Z / adj (NCCL, outside this library); saver_cuda_cor_block
+// then fills one rectangular block of the adjusted correlation from the gathered panel.
+extern "C" int saver_cuda_cor_prep(saver_cuda_handle h, const double* est, const double* se, int n,
+                                   int B, double* Z, int ldz, double* adj, int device_ptrs) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!est || !se || !Z || !adj || n < 2 || B < 0 || ldz < n || ldz % 16 != 0)
+    return fail(h, SAVER_ERR_ARG, "cor_prep: bad arguments (ldz must be a multiple of 16 >= n)");
+  if (B == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  const bool dev = device_ptrs != 0;
+  cudaStream_t s = h->stream;
+  InArr<double> dE, dS;
+  OutArr<double> dZ, dA;
+  CU(dE.bind(est, (size_t)n * B, dev, s));
+  CU(dS.bind(se, (size_t)n * B, dev, s));
+  CU(dZ.bind(Z, (size_t)ldz * B, dev, s));
+  CU(dA.bind(adj, (size_t)B, dev, s));
+  cor_prep_kernel<<<B, 256, 0, s>>>(dE.d, dS.d, n, ldz, dZ.d, dA.d);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(dZ.fetch(s));
+  CU(dA.fetch(s));
+  if (!dev) CU(cudaStreamSynchronize(s));
+  return SAVER_OK;
+}
+
+extern "C" int saver_cuda_cor_block(saver_cuda_handle h, const double* Z, int ldz, const double* adj,
+                                    int M, int row0, int nrows, int col0, int ncols, double* out,
+                                    int ldo) {
+  if (!h) return SAVER_ERR_ARG;
+  if (!Z || !adj || !out || ldz % 16 != 0 || M < 1 || row0 < 0 || nrows < 0 || row0 + nrows > M ||
+      col0 < 0 || ncols < 0 || col0 + ncols > M || ldo < row0 + nrows)
+    return fail(h, SAVER_ERR_ARG, "cor_block: bad arguments");
+  if (nrows == 0 || ncols == 0) return SAVER_OK;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  // device pointers only; Z must be allocated (and zero filled) up to round_up(M, 128) + 64 columns:
+  // the GEMM reads whole tiles
+  double* C = out + row0;
+  CU(launch_gemm_tn_f64(Z + (size_t)ldz * row0, ldz, Z + (size_t)ldz * col0, ldz, C, ldo, nrows, ncols, ldz, s));
+  cor_scale_kernel<<<kGrid, 256, 0, s>>>(C, ldo, nrows, ncols, adj + row0, adj + col0, nullptr, 0);
+  CU(cudaGetLastError());
+  h->launches += 2;
   return SAVER_OK;
 }

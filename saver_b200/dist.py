@@ -80,6 +80,26 @@ class Comm:
         self.bytes_broadcast += t.numel() * t.element_size()
         return t if keep_on_device else t.cpu().numpy()
 
+    def allgather_blocks(self, t, sizes):
+        """Row blocks of one matrix, block r ((sizes[r], k) float64 tensor on self.device) held by rank
+        r -> the stacked matrix plus `pad` zero rows on every rank, as ONE all-gather into a tensor
+        (equal blocks) or a list all-gather of padded blocks.  Stays on the device."""
+        torch = self.torch
+        sizes = [int(v) for v in sizes]
+        k = t.shape[1] if t.dim() == 2 else 1
+        tot, mx = sum(sizes), max(sizes)
+        if min(sizes) == mx:
+            out = torch.empty((tot,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            self.dist.all_gather_into_tensor(out, t.contiguous())
+        else:
+            padded = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            padded[:t.shape[0]] = t
+            parts = [torch.empty_like(padded) for _ in range(self.world)]
+            self.dist.all_gather(parts, padded)
+            out = torch.cat([p[:sizes[r]] for r, p in enumerate(parts)], 0)
+        self.bytes_gathered += tot * k * t.element_size()
+        return out
+
     def max_scalar(self, v):
         t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)

@@ -812,6 +812,65 @@ def cor_genes(x, cor_mat=None, handle=None, comm=None, gather=True):
     return _cor_adjust(x, False, cor_mat, handle, comm, gather)
 
 
+def cyclic_window(rank, world):
+    """Row blocks rank `rank` computes of its column panel of a symmetric matrix split into
+    world x world blocks: its own block and the next world // 2 in cyclic order (for an even world
+    the farthest block only on the lower half of the ranks) -- every unordered pair of blocks is
+    computed exactly once and every rank does the same amount of work to within one block."""
+    half = world // 2
+    blocks = [(rank + d) % world for d in range(half + 1)]
+    if world % 2 == 0 and world > 1 and rank >= half:
+        blocks = blocks[:-1]
+    return blocks
+
+
+def cor_genes_sharded(est, se, comm, handle=None, symmetric=True):
+    """cor.genes (R/cor_adjust.R:26-44) on a gene-sharded saver object: rank r holds the rows
+    (est, se: (B_r, n) CUDA tensors or arrays) of ITS genes, blocks stacked in rank order.
+
+    Every rank standardises its own rows, ONE all-gather ships the standardised panel and adj, and
+    the rank fills its column panel of the adjusted correlation -- with ``symmetric`` only the row
+    blocks of cyclic_window(rank, world), the rest being the transposes of blocks other ranks own.
+    Returns (panel, (c0, c1), blocks): panel (B_r, G) CUDA tensor = rows c0..c1 of the matrix,
+    blocks = [(r0, r1)] column ranges of the panel that were computed."""
+    import torch
+    dev = comm.device
+    on_gpu = dev.type == "cuda"
+    h = (handle or ops.default_handle()) if on_gpu else handle
+
+    def sync():   # the library runs on its own stream, the collectives on torch's
+        if on_gpu:
+            h.synchronize()
+            torch.cuda.synchronize()
+
+    est = est if hasattr(est, "is_cuda") else torch.from_numpy(np.ascontiguousarray(est))
+    se = se if hasattr(se, "is_cuda") else torch.from_numpy(np.ascontiguousarray(se))
+    est, se = est.to(dev).contiguous(), se.to(dev).contiguous()
+    sizes = torch.zeros(comm.world, dtype=torch.int64, device=dev)
+    sizes[comm.rank] = est.shape[0]
+    comm.dist.all_reduce(sizes)
+    sizes = [int(v) for v in sizes.cpu().numpy()]
+    edges = np.concatenate([[0], np.cumsum(sizes)])
+    G = int(edges[-1])
+    Z, adj = ops.cor_prep(est, se, handle=h)
+    sync()
+    Zall = comm.allgather_blocks(Z, sizes)
+    adj_all = comm.allgather_blocks(adj, sizes)
+    Zall = torch.cat([Zall, torch.zeros((128, Zall.shape[1]), dtype=Zall.dtype, device=dev)], 0)
+    c0, c1 = int(edges[comm.rank]), int(edges[comm.rank + 1])
+    panel = torch.zeros((c1 - c0, G), dtype=torch.float64, device=dev)
+    todo = cyclic_window(comm.rank, comm.world) if symmetric else list(range(comm.world))
+    blocks = []
+    sync()
+    for b in todo:
+        r0, r1 = int(edges[b]), int(edges[b + 1])
+        if r1 > r0 and c1 > c0:
+            ops.cor_block(Zall, adj_all, G, r0, r1 - r0, c0, c1 - c0, panel, handle=h)
+            blocks.append((r0, r1))
+    sync()
+    return panel, (c0, c1), blocks
+
+
 def cor_cells(x, cor_mat=None, handle=None, comm=None, gather=True):
     """cor.cells (R/cor_adjust.R:48-66); ``comm`` / ``gather`` as in cor_genes."""
     return _cor_adjust(x, True, cor_mat, handle, comm, gather)

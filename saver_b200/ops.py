@@ -275,6 +275,38 @@ def cor_adjust(est, se, by_cells=False, cor_in=None, col0=0, ncols=None, handle=
     return out
 
 
+def cor_prep(est, se, handle=None):
+    """First half of cor.genes for a block of genes: est, se (B, n) -> Z (B, ldz) centred unit-norm
+    rows (ldz = n rounded up to 16, zero padded), adj (B).  Device tensors stay on the device."""
+    h = handle or default_handle()
+    dev = is_device(est)
+    B, n = est.shape
+    ldz = (n + 15) // 16 * 16
+    if dev:
+        import torch
+        Z = torch.empty((B, ldz), dtype=torch.float64, device=est.device)
+        adj = torch.empty((B,), dtype=torch.float64, device=est.device)
+    else:
+        est, se = _f64(est), _f64(se)
+        Z, adj = np.empty((B, ldz)), np.empty(B)
+    h.check(h.lib.saver_cuda_cor_prep(h.h, ptr(est), ptr(se), n, B, ptr(Z), ldz, ptr(adj), int(dev)))
+    return Z, adj
+
+
+def cor_block(Z, adj, M, row0, nrows, col0, ncols, out, handle=None):
+    """Second half: out[c, row0:row0+nrows] (out: (ncols, >= row0+nrows) device tensor, one row per
+    column c of [col0, col0+ncols)) = adjusted correlation block from the gathered panel Z
+    ((>= M + 128, ldz) device tensor, rows beyond M zero), adj (M)."""
+    h = handle or default_handle()
+    if not (is_device(Z) and is_device(adj) and is_device(out)):
+        raise ValueError("cor_block works on device tensors")
+    if Z.shape[0] < M + 128:
+        raise ValueError("Z needs M + 128 rows (zero filled beyond M): the GEMM reads whole tiles")
+    h.check(h.lib.saver_cuda_cor_block(h.h, ptr(Z), int(Z.shape[1]), ptr(adj), int(M), int(row0),
+                                       int(nrows), int(col0), int(ncols), ptr(out), int(out.shape[1])))
+    return out
+
+
 def set_counts_csc(x, handle=None):
     """Upload a scipy.sparse genes x cells matrix (kept resident; R's dgCMatrix layout)."""
     h = handle or default_handle()

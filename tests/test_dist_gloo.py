@@ -167,3 +167,82 @@ def test_two_rank_sharding_is_result_invariant(tmp_path):
         merged[d["ro_own"]] = d["ro_est"][d["ro_own"]]
         assert np.array_equal(d["ro_lmin"], sub.info["lambda.min"])   # stage scalars reach every rank
     assert np.array_equal(merged, sub.estimate)                        # the slices tile the one-rank result
+
+
+def _cpu_cor_ops(ops):
+    """numpy stand-ins with the contract of saver_cuda_cor_prep / saver_cuda_cor_block."""
+    import torch
+
+    def cor_prep(est, se, handle=None):
+        e, s = est.numpy(), se.numpy()
+        B, n = e.shape
+        ldz = (n + 15) // 16 * 16
+        d = e - e.mean(1, keepdims=True)
+        ss = (d ** 2).sum(1)
+        Z = np.zeros((B, ldz))
+        Z[:, :n] = d / np.sqrt(ss)[:, None]
+        var = ss / (n - 1)
+        return torch.from_numpy(Z), torch.from_numpy(np.sqrt(var / (var + (s ** 2).mean(1))))
+
+    def cor_block(Z, adj, M, row0, nrows, col0, ncols, out, handle=None):
+        assert Z.shape[0] >= M + 128 and not Z[M:].any()
+        z, a = Z.numpy(), adj.numpy()
+        c = np.clip(z[col0:col0 + ncols] @ z[row0:row0 + nrows].T, -1.0, 1.0)
+        out[:, row0:row0 + nrows] = torch.from_numpy(c * np.outer(a[col0:col0 + ncols], a[row0:row0 + nrows]))
+        return out
+
+    ops.cor_prep, ops.cor_block = cor_prep, cor_block
+
+
+def _cor_sharded_worker(rank, world, port, outdir, equal):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from saver_b200 import dist, host, ops
+    _cpu_cor_ops(ops)
+    comm = dist.Comm(backend="gloo")
+    est, se = _posthoc_inputs()
+    if equal:
+        est, se = est[:12], se[:12]
+    rows = np.array_split(np.arange(est.shape[0]), world)[rank]
+    panel, (c0, c1), blocks = host.cor_genes_sharded(est[rows], se[rows], comm)
+    assert (c0, c1) == (rows[0], rows[-1] + 1) and panel.shape == (rows.size, est.shape[0])
+    np.savez(os.path.join(outdir, "cs%d.npz" % rank), panel=panel.numpy(), c=np.array([c0, c1]),
+             blocks=np.array(blocks))
+    comm.barrier()
+
+
+@pytest.mark.parametrize("world,equal", [(2, False), (3, False), (4, True)])
+def test_cor_genes_sharded_tiles_the_symmetric_matrix(tmp_path, world, equal):
+    """cor.genes on a gene-sharded object: all-gather of the standardised rows,
+    every unordered pair of gene blocks computed by exactly one rank; the blocks and their
+    transposes tile the one-rank result."""
+    from oracle import posthoc
+    port = 29700 + (os.getpid() % 90) + 7 * world
+    mp.spawn(_cor_sharded_worker, args=(world, port, str(tmp_path), equal), nprocs=world, join=True)
+    est, se = _posthoc_inputs()
+    if equal:
+        est, se = est[:12], se[:12]
+    want = posthoc.cor_adjust(est, se)
+    G = est.shape[0]
+    full, seen = np.zeros((G, G)), np.zeros((G, G), dtype=int)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), "cs%d.npz" % r))
+        c0, c1 = d["c"]
+        for r0, r1 in d["blocks"]:
+            full[c0:c1, r0:r1] = d["panel"][:, r0:r1]
+            seen[c0:c1, r0:r1] += 1
+            if (r0, r1) != (c0, c1):
+                full[r0:r1, c0:c1] = d["panel"][:, r0:r1].T
+                seen[r0:r1, c0:c1] += 1
+    assert (seen == 1).all()
+    assert np.allclose(full, want, rtol=1e-12, atol=1e-14)
+
+
+def test_cyclic_window_covers_every_block_pair_once():
+    from saver_b200 import host
+    for world in range(1, 10):
+        pairs = [tuple(sorted((r, b))) for r in range(world) for b in host.cyclic_window(r, world)]
+        assert sorted(pairs) == sorted((a, b) for a in range(world) for b in range(a, world))
+        work = [len(host.cyclic_window(r, world)) for r in range(world)]
+        assert max(work) - min(work) <= 1

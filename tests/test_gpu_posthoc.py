@@ -109,3 +109,33 @@ def test_legacy_alpha_beta_objects_use_the_same_kernels(handle):
     mu, size = 4.5 / 0.03, 4.5
     assert abs(k.mean() - mu) < 5 * np.sqrt((mu + mu * mu / size) / k.size)
     assert (k == np.rint(k)).all()
+
+
+def test_cor_prep_and_blocks_tile_cor_genes(golden, handle):
+    """saver_cuda_cor_prep + saver_cuda_cor_block (the gene-sharded cor.genes of SURVEY.md 8(e)(4)):
+    blocks filled from a standardised panel reproduce saver_cuda_cor_adjust, upper-triangle blocks +
+    their transposes give the whole symmetric matrix."""
+    import torch
+    obj = _golden_obj(golden)
+    est, se = obj.estimate[:333], obj.se[:333]
+    G, n = est.shape
+    want = ops.cor_adjust(est, se, handle=handle)
+    dev = torch.device("cuda", handle.device)
+    Z, adj = ops.cor_prep(torch.from_numpy(est).to(dev), torch.from_numpy(se).to(dev), handle=handle)
+    handle.synchronize()
+    assert Z.shape == (G, (n + 15) // 16 * 16) and not Z[:, n:].any()
+    assert np.allclose((Z * Z).sum(1).cpu().numpy(), 1.0, rtol=1e-12)
+    Zp = torch.cat([Z, torch.zeros((128, Z.shape[1]), dtype=Z.dtype, device=dev)], 0)
+    full = torch.zeros((G, G), dtype=torch.float64, device=dev)
+    ed = [0, 100, 101, 260, G]
+    torch.cuda.synchronize()
+    for i in range(4):
+        for j in range(i, 4):
+            ops.cor_block(Zp, adj, G, ed[j], ed[j + 1] - ed[j], ed[i], ed[i + 1] - ed[i],
+                          full[ed[i]:ed[i + 1]], handle=handle)
+    handle.synchronize()
+    got = full.cpu().numpy()
+    got = np.triu(got) + np.triu(got, 1).T
+    assert np.abs(got - want).max() < 1e-12
+    with pytest.raises(ValueError):
+        ops.cor_block(Z, adj, G, 0, G, 0, G, full, handle=handle)   # panel without the zero tile rows
