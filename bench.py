@@ -52,6 +52,7 @@ WORKLOADS = {
     "null": dict(G=20000, n=10000, seed=20263, block=0),
     "fast": dict(G=5000, n=2000, seed=20262, block=0),
     "cfg5": dict(G=20000, n=10000, seed=20265, block=0),
+    "cfg4": dict(G=30000, n=50000, seed=20264, block=2048),
 }
 METRIC = "genes/sec, full saver() (cv Poisson lasso + variance fit + posterior), synthetic NB"
 
@@ -579,7 +580,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     args = ap.parse_args()
     try:
-        if args.workload in ("null", "fast", "cfg5") and args.impl == "cuda":
+        if args.workload in ("null", "fast", "cfg5", "cfg4") and args.impl == "cuda":
             import bench_extra
             bench_extra.run(args)
         elif args.impl == "reference":

@@ -73,6 +73,8 @@ def run(args):
         run_null(args)
     elif args.workload == "fast":
         run_fast(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
     else:
         run_cfg5(args)
 
@@ -232,6 +234,102 @@ def run_fast(args):
         }
         print(json.dumps(line), flush=True)
     _finish(comm)
+
+
+# ------------------------------------------------------------------------------------------------
+def sparse_nb_counts(G, n, seed, dev, torch, chunk=2000, k=12):
+    """synth.nb_counts' model drawn on the device cell-chunk by cell-chunk and assembled straight into
+    the three slots of a dgCMatrix (genes x cells, compressed by cell) -- a 30k x 50k matrix never
+    exists densely on the host."""
+    import scipy.sparse as sp
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    f64 = torch.float64
+    W = torch.randn((G, k), generator=gen, device=dev, dtype=f64) * 0.5
+    W[torch.rand(G, generator=gen, device=dev) < 0.3] = 0.0
+    b = torch.randn(G, generator=gen, device=dev, dtype=f64) * 1.5 - 1.0
+    phi = torch.clamp(torch._standard_gamma(torch.full((G,), 2.0, device=dev, dtype=f64), generator=gen), 0.1, 50.0)
+    data, idx, counts = [], [], []
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        Z = torch.randn((c1 - c0, k), generator=gen, device=dev, dtype=f64)
+        depth = torch.exp(torch.randn(c1 - c0, generator=gen, device=dev, dtype=f64) * 0.35)
+        rate = torch.exp(b[None, :] + Z @ W.T) * depth[:, None]            # cells x genes
+        lam = torch._standard_gamma(phi[None, :].expand_as(rate).contiguous(), generator=gen) * rate / phi[None, :]
+        xt = torch.poisson(lam, generator=gen)
+        nz = xt != 0
+        counts.append(nz.sum(1).cpu())
+        cg = nz.nonzero()                                                    # sorted by cell, then gene
+        idx.append(cg[:, 1].to(torch.int32).cpu())
+        data.append(xt[nz].cpu())
+        del rate, lam, xt, nz, cg
+    indptr = np.concatenate([[0], np.cumsum(torch.cat(counts).numpy())]).astype(np.int64)
+    return sp.csc_matrix((torch.cat(data).numpy(), torch.cat(idx).numpy(), indptr), shape=(G, n))
+
+
+def run_cfg4(args):
+    """BASELINE.json configs[3]: sparse dgCMatrix 30k genes x 50k cells, library-size size factors,
+    estimates.only = FALSE.  A step = saver(x, pred.genes = block, pred.genes.only = TRUE) with the
+    default do.fast schedule on a fixed gene block of the matrix (the whole matrix is the design)."""
+    import bench
+    import saver_b200
+    from saver_b200 import host
+    torch, rank, world, local, dev, comm = _env()
+    if comm is not None:
+        raise SystemExit("cfg4 is a one-GPU line")
+    h = saver_b200.Handle(local)
+    G, n = 30000, 50000
+    block = 2048 if args.block is None else args.block
+    t0 = time.time()
+    x = sparse_nb_counts(G, n, 20264, dev, torch)
+    t_gen = time.time() - t0
+    torch.cuda.empty_cache()
+    pred = np.where(np.asarray(x.sum(1)).ravel() > 0)[0]
+    genes = bench.pick_block(pred, block)
+    be = host.CudaBackend(handle=h)
+    kw = dict(do_fast=True, estimates_only=False, fold_seed=args.fold_seed, perm=args.fold_seed,
+              pred_genes_only=True, backend=be)
+    clocks = bench.ClockSampler(local)
+    times, res = [], None
+    l0 = h.launch_count()
+    for it in range(args.steps + 1):   # the first pass (a few genes) warms the path
+        h.synchronize()
+        if it == 1:
+            clocks.start()
+            l0 = h.launch_count()
+        t0 = time.time()
+        res = saver_b200.saver(x, pred_genes=genes if it else genes[:32], **kw)
+        h.synchronize()
+        if it:
+            times.append(time.time() - t0)
+    clk = clocks.stop()
+    info = res.info
+    ncv = int((np.isfinite(info["sd.cv"]) & (info["lambda.max"] > 0)).sum())
+    nfix = int(np.isnan(info["sd.cv"]).sum())
+    tot = float(np.sum(times))
+    B = genes.size
+    line = {
+        "metric": "genes/sec, saver(dgCMatrix, estimates.only = FALSE), synthetic NB 30k x 50k",
+        "value": B * args.steps / tot, "unit": "genes/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": 1, "ms_per_step": tot * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: sparse dgCMatrix %d genes x %d cells (nnz %d = %.0f %% dense), library-size "
+                               "size factors, do.fast=TRUE, estimates.only=FALSE, %d predictors; a step = a fixed "
+                               "block of %d genes: %d cross-validated, %d fixed-lambda paths, the rest means"
+                               % (G, n, x.nnz, 100.0 * x.nnz / (G * n), int((np.asarray(x.mean(1)).ravel() >= 0.1).sum()),
+                                  B, ncv, nfix)},
+        "clocks": clk,
+        "e2e": {"value": B * args.steps / tot, "unit": "genes/s",
+                "h2d_bytes_per_step": int(x.data.nbytes + x.indices.nbytes + x.indptr.nbytes),
+                "d2h_bytes_per_step": int(res.estimate.nbytes * 2), "s_per_step": tot / args.steps,
+                "api": "saver_b200.saver(scipy CSC on the host, pred_genes=block, pred_genes_only=True): the value "
+                       "IS the end-to-end number (CSC upload, device sums / design, stage schedule, est + se D2H)"},
+        "gpu_launches": int(h.launch_count() - l0),
+        "roofline": None,
+        "status_counts": np.bincount(res.status, minlength=3).tolist() if hasattr(res, "status") else None,
+        "generate_s": t_gen,
+    }
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------

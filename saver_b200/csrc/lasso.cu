@@ -53,6 +53,7 @@ void LassoTuning::from_env() {
   geti("SAVER_LASSO_F32", f32);
   if (const char* e = getenv("SAVER_GRAM_HS")) gram_hs = atol(e);
   if (const char* e = getenv("SAVER_STRONG_SLACK")) strong_slack = atof(e);
+  if (const char* e = getenv("SAVER_CHORD_TOL")) chord_tol = atof(e);
 }
 
 void LassoWs::release() {
@@ -328,6 +329,7 @@ __global__ void lasso_snapshot_kernel(RoundArgs A) {
 // the round kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kMeta = 64;  // strong-set metadata staged per chunk
+constexpr int kChordKeep = 4;   // IRLS steps of one launch that may reuse the launch's first Gram block
 constexpr int kPart = 512;        // doubles: partial sums of the row-split streaming work items
 constexpr int kHSlots = 148 * 4;  // Gram scratch slots (>= resident CTAs of the gram kernel)
 constexpr int kGramSmem = kMeta * 8 + 3 * kNX * 8 + 64 + kNX * 4 - kNX * 8 + kMeta * 4 + kPart * 8;  // mg, gq, gq2, amat, gsh, ord, mamb, part; as_ lives in global memory
@@ -592,6 +594,8 @@ lasso_round_kernel(RoundArgs A, const int* __restrict__ list, int* __restrict__ 
   };
 
   if (state == ST_SOLVE) {
+    int irls_it = 0;
+    bool big_step = false;
     while (true) {  // IRLS iterations
       const double az0 = az;
       for (int l = tid; l < nin; l += T) as_[l] = aact[l];
@@ -2269,6 +2273,8 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       ord[rank] = l;
     }
     __syncthreads();
+    int irls_it = 0;
+    bool big_step = false;
     while (true) {  // IRLS iterations
       const double az0 = az;
       for (int l = tid; l < nin; l += T) {
@@ -2289,7 +2295,12 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         // cycle): the fixed point only depends on the gradient, the model only shapes the step
         // (chord iteration).  A variable entering under a stale model triggers a rebuild.
         lap(3);
-        const bool rebuild = !H_valid || (dbg & 64);
+        // ... unless the previous IRLS step was large (big_step) or the iteration drags on: with a
+        // coarse lambda step (the fixed-lambda variant's factor e^-0.2) the weights move so far
+        // from those of the kept model that the chord iteration oscillates up to maxit
+        // (scripts/probe_heavy.py); then the model is rebuilt (plain IRLS, as fishnet1 does).
+        const bool rebuild = !H_valid || big_step || irls_it >= kChordKeep || (dbg & 64);
+        ++irls_it;
         gram_vectors(0, m, rebuild);
         lap(1);
         if (rebuild) {
@@ -2421,16 +2432,20 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       cur_dev = (acc[1] - v0 - dv0) / dvr;
       cur_cv = acc[3];
       // ---- outer convergence (fishnet1: intercept and every active coefficient) ----
-      int bad = v0 * (az - az0) * (az - az0) >= shr;
+      double chg = v0 * (az - az0) * (az - az0);
       for (int l = tid; l < nin; l += T) {
         const double d = aact[l] - as_[l];
-        bad |= va[l] * d * d >= shr;
+        chg = fmax(chg, va[l] * d * d);
       }
+      chg = bmax(chg, red, phase);
       lap(6);
-      if (!__syncthreads_or(bad)) {
+      if (!(chg >= shr)) {
         state = ST_WAIT_KKT;
         break;
       }
+      // the step just taken says how far the working weights moved: a large one makes the kept
+      // model a poor chord (coarse lambda steps: the iteration then oscillates up to maxit)
+      big_step = chg > A.prm.chord_tol * shr;
     }
   }
 
@@ -2813,6 +2828,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   const LassoTuning& tune = ws.tune;
   if (tune.dbg >= 0) A.prm.dbg = tune.dbg;
   if (tune.strong_slack >= 0) A.prm.strong_slack = tune.strong_slack;
+  if (tune.chord_tol >= 0) A.prm.chord_tol = tune.chord_tol;
   if ((A.prm.dbg & 4096) && !ws.h_crumb) {
     if ((e = cudaHostAlloc(&ws.h_crumb, (size_t)kCrumbSlots * 32, cudaHostAllocMapped)) != cudaSuccess) return e;
     memset(ws.h_crumb, 0, (size_t)kCrumbSlots * 32);

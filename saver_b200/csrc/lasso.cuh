@@ -51,6 +51,8 @@ struct LassoParams {
   int gram = 1;     // 1: Gram-space round kernel (default), 0: n-space kernel that mirrors fishnet1's iterate sequence
   double strong_slack = 1.0;  // screening margin below lambda in units of the lambda step (1 = strong rule)
   double inner_scale = 1.0;   // Gram kernel: the sweeps inside one IRLS step stop at thr * inner_scale * dev0
+  double chord_tol = 1.0e4;   // Gram kernel: an IRLS step that moved a coefficient by more than chord_tol x
+                              // the convergence threshold invalidates the kept curvature model
   int dbg = 0;      // bisection switches for bring-up (SAVER_LASSO_DBG), 0 in production
 };
 
@@ -67,6 +69,7 @@ struct LassoTuning {
   long gram_hs = -1;       // SAVER_GRAM_HS: cap (bytes) of the packed Gram block in shared memory
   int l2_persist = -1;     // SAVER_L2_PERSIST: 0 = no persisting-L2 window on the design
   double strong_slack = -1.0;  // SAVER_STRONG_SLACK
+  double chord_tol = -1.0; // SAVER_CHORD_TOL
   int f32 = -1;            // SAVER_LASSO_F32: 0 = the curvature model reads the FP64 design too
   int order = -1;          // SAVER_LASSO_ORDER: 0 completion order, 1 fits of a gene adjacent, 2 + one cluster per gene
   void from_env();

@@ -165,3 +165,31 @@ def test_time_slices_resume_to_the_same_solution(handle, monkeypatch):
     assert np.mean(cut["idx"] == ref["idx"]) >= 0.9
     same = cut["idx"] == ref["idx"]
     assert np.median(_rel(cut["mu"][same], ref["mu"][same])) < 1e-4
+
+
+def test_fixed_lambda_path_converges_on_coarse_lambda_steps(handle):
+    """The fixed-lambda variant steps lambda by e^-0.2 (R/expr_predict.R:62-63): on these six genes of
+    a 1,200 x 2,000 synthetic matrix (tests/golden/fastpath_heavy.npz, found by
+    scripts/probe_fastpath.py) the Gram kernel's kept curvature model used to oscillate up to maxit
+    (glmnet jerr = -lambda index, a truncated path) where fishnet1 needs a few hundred sweeps."""
+    from saver_b200 import host
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "fastpath_heavy.npz"))
+    G, n = int(d["G"]), int(d["n"])
+    x = synth.nb_counts(G, n, 20264).astype(np.float64)
+    xc, _ = host.clean_data(x)
+    sf, _ = host.calc_size_factor(xc, None, n)
+    good = np.where(xc.mean(1) >= 0.1)[0]
+    x_est = np.log((xc[good] + 1.0) / sf)
+    self_col = np.full(G, -1, dtype=np.int32)
+    self_col[good] = np.arange(good.size, dtype=np.int32)
+    genes = d["genes"]
+    y = xc[genes] / sf
+    handle.set_option("lasso_gram", 1)
+    ops.set_design(x_est, handle=handle)
+    got = ops.predict_path(y, d["lmax"], d["lmin"], self_col=self_col[genes], want_stats=True, handle=handle)
+    ref = oracle.predict_path_batch(x_est, y, d["lmax"], d["lmin"], self_col=self_col[genes])
+    st = np.asarray(got["stats"])
+    assert (got["status"] == 0).all() and (st[:, 1] == 0).all(), st
+    assert (st[:, 0] == ref["lmu"]).all()
+    assert (st[:, 2] < 3 * np.maximum(ref["nlp"], 300)).all(), (st[:, 2], ref["nlp"])
+    assert np.median(_rel(got["mu"], ref["mu"])) < 1e-3
