@@ -278,7 +278,7 @@ def run_cfg4(args):
     if comm is not None:
         raise SystemExit("cfg4 is a one-GPU line")
     h = saver_b200.Handle(local)
-    G, n = 30000, 50000
+    G, n = int(os.environ.get("CFG4_G", 30000)), int(os.environ.get("CFG4_N", 50000))   # env: smoke sizes
     block = 2048 if args.block is None else args.block
     t0 = time.time()
     x = sparse_nb_counts(G, n, 20264, dev, torch)
@@ -309,7 +309,7 @@ def run_cfg4(args):
     tot = float(np.sum(times))
     B = genes.size
     line = {
-        "metric": "genes/sec, saver(dgCMatrix, estimates.only = FALSE), synthetic NB 30k x 50k",
+        "metric": "genes/sec, saver(dgCMatrix, estimates.only = FALSE), synthetic NB %dk x %dk" % (G // 1000, n // 1000),
         "value": B * args.steps / tot, "unit": "genes/s", "n_gpus": 1, "steps": args.steps,
         "warmup": 1, "ms_per_step": tot * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
