@@ -1723,18 +1723,38 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     crumb(16);
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5, g8 = lane >> 2, t4 = lane & 3;
     const int T16 = (m + 15) >> 4, ntile = T16 * (T16 + 1) / 2;
-    for (int tix = warp; tix < ntile; tix += nw) {
-      int J = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+    // ntile tiles on nw warps leave the CTA waiting for the warps with one tile more (16 % of all
+    // stall samples sat at this phase's closing barrier, profiles/r2_ncu_lasso_lines.txt): tiles are
+    // cut into S row segments, S minimising rounds / S, partial tiles summed in a fixed order.
+    int S = 1;
+    if (!(A.prm.dbg & 65536)) {
+      int bn = (ntile + nw - 1) / nw;  // best cost = bn / S
+      for (int s2 = 2; s2 <= 16; ++s2) {
+        if (ntile * s2 > kGramItems || s2 * 512 > ldx) break;
+        const int c = (ntile * s2 + nw - 1) / nw;
+        if (c * S < bn * s2) { bn = c; S = s2; }
+      }
+    }
+    const int sl = ((ldx + S - 1) / S + 15) & ~15;
+    double* HPc = A.ws.HP + (size_t)hslot * kGramItems * 256;
+    auto decode = [&](int tix, int& I, int& J) {
+      J = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
       while ((J + 1) * (J + 2) / 2 <= tix) ++J;
       while (J * (J + 1) / 2 > tix) --J;
-      const int I = tix - J * (J + 1) / 2;
+      I = tix - J * (J + 1) / 2;
+    };
+    for (int item = warp; item < ntile * S; item += nw) {
+      const int tix = item / S, seg = item - tix * S;
+      const int r0 = seg * sl, r1 = r0 + sl < ldx ? r0 + sl : ldx;
+      int I, J;
+      decode(tix, I, J);
       double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
       if (Xf) {  // FP32 copy: 16 rows per step, four k-slices of one 16-byte load per lane
         auto colf = [&](int idx) { return Xf + (size_t)ia[idx < m ? idx : m - 1] * ldx + 4 * t4; };
         const float *fI0 = colf(I * 16 + g8), *fI1 = colf(I * 16 + 8 + g8);
         const float *fJ0 = colf(J * 16 + g8), *fJ1 = colf(J * 16 + 8 + g8);
 #pragma unroll 2
-        for (int base = 0; base < ldx; base += 16) {
+        for (int base = r0; base < r1; base += 16) {
           const float4 a0 = __ldg(reinterpret_cast<const float4*>(fI0 + base));
           const float4 a1 = __ldg(reinterpret_cast<const float4*>(fI1 + base));
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(fJ0 + base));
@@ -1754,40 +1774,63 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
           }
         }
       } else {
-      auto colp = [&](int idx) { return Xs + (size_t)ia[idx < m ? idx : m - 1] * ldx + 2 * t4; };
-      const double *cI0 = colp(I * 16 + g8), *cI1 = colp(I * 16 + 8 + g8);
-      const double *cJ0 = colp(J * 16 + g8), *cJ1 = colp(J * 16 + 8 + g8);
+        auto colp = [&](int idx) { return Xs + (size_t)ia[idx < m ? idx : m - 1] * ldx + 2 * t4; };
+        const double *cI0 = colp(I * 16 + g8), *cI1 = colp(I * 16 + 8 + g8);
+        const double *cJ0 = colp(J * 16 + g8), *cJ1 = colp(J * 16 + 8 + g8);
 #pragma unroll 2
-      for (int base = 0; base < ldx; base += 8) {
-        const double2 a0 = ldg2(cI0 + base), a1 = ldg2(cI1 + base);
-        double2 b0 = ldg2(cJ0 + base), b1 = ldg2(cJ1 + base);
-        const double2 w = *reinterpret_cast<const double2*>(wv + base + 2 * t4);
-        b0.x *= w.x; b0.y *= w.y; b1.x *= w.x; b1.y *= w.y;
-        dmma(acc[0][0][0], acc[0][0][1], a0.x, b0.x);
-        dmma(acc[0][1][0], acc[0][1][1], a0.x, b1.x);
-        dmma(acc[1][0][0], acc[1][0][1], a1.x, b0.x);
-        dmma(acc[1][1][0], acc[1][1][1], a1.x, b1.x);
-        dmma(acc[0][0][0], acc[0][0][1], a0.y, b0.y);
-        dmma(acc[0][1][0], acc[0][1][1], a0.y, b1.y);
-        dmma(acc[1][0][0], acc[1][0][1], a1.y, b0.y);
-        dmma(acc[1][1][0], acc[1][1][1], a1.y, b1.y);
+        for (int base = r0; base < r1; base += 8) {
+          const double2 a0 = ldg2(cI0 + base), a1 = ldg2(cI1 + base);
+          double2 b0 = ldg2(cJ0 + base), b1 = ldg2(cJ1 + base);
+          const double2 w = *reinterpret_cast<const double2*>(wv + base + 2 * t4);
+          b0.x *= w.x; b0.y *= w.y; b1.x *= w.x; b1.y *= w.y;
+          dmma(acc[0][0][0], acc[0][0][1], a0.x, b0.x);
+          dmma(acc[0][1][0], acc[0][1][1], a0.x, b1.x);
+          dmma(acc[1][0][0], acc[1][0][1], a1.x, b0.x);
+          dmma(acc[1][1][0], acc[1][1][1], a1.x, b1.x);
+          dmma(acc[0][0][0], acc[0][0][1], a0.y, b0.y);
+          dmma(acc[0][1][0], acc[0][1][1], a0.y, b1.y);
+          dmma(acc[1][0][0], acc[1][0][1], a1.y, b0.y);
+          dmma(acc[1][1][0], acc[1][1][1], a1.y, b1.y);
+        }
       }
-      }
+      if (S == 1) {
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+          for (int b = 0; b < 2; ++b)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = I * 16 + a * 8 + g8, cc = J * 16 + b * 8 + 2 * t4 + e;
-            if (r < m && cc < m && (I != J || r <= cc)) {
-              H[r + (size_t)cc * ldh] = acc[a][b][e];
-              H[cc + (size_t)r * ldh] = acc[a][b][e];
+            for (int e = 0; e < 2; ++e) {
+              const int r = I * 16 + a * 8 + g8, cc = J * 16 + b * 8 + 2 * t4 + e;
+              if (r < m && cc < m && (I != J || r <= cc)) {
+                H[r + (size_t)cc * ldh] = acc[a][b][e];
+                H[cc + (size_t)r * ldh] = acc[a][b][e];
+              }
             }
-          }
+      } else {
+        double2* dst = reinterpret_cast<double2*>(HPc + ((size_t)item * 32 + lane) * 8);
+        dst[0] = make_double2(acc[0][0][0], acc[0][0][1]);
+        dst[1] = make_double2(acc[0][1][0], acc[0][1][1]);
+        dst[2] = make_double2(acc[1][0][0], acc[1][0][1]);
+        dst[3] = make_double2(acc[1][1][0], acc[1][1][1]);
+      }
     }
     gram_fma += (unsigned long long)ntile * 256ull * (unsigned)ldx;
     __syncthreads();
+    if (S > 1) {
+      for (int idx = tid; idx < ntile * 256; idx += T) {
+        const int tix = idx >> 8, ln = (idx >> 3) & 31, k = idx & 7;
+        double v = 0.0;
+        for (int seg = 0; seg < S; ++seg) v += HPc[((size_t)(tix * S + seg) * 32 + ln) * 8 + k];
+        int I, J;
+        decode(tix, I, J);
+        const int r = I * 16 + (k >> 2) * 8 + (ln >> 2), cc = J * 16 + ((k >> 1) & 1) * 8 + 2 * (ln & 3) + (k & 1);
+        if (r < m && cc < m && (I != J || r <= cc)) {
+          H[r + (size_t)cc * ldh] = v;
+          H[cc + (size_t)r * ldh] = v;
+        }
+      }
+      __syncthreads();
+    }
   };
   // per-fit standardisation of the raw moments: H and v (-> va) ...
   auto gram_finish_H = [&](int m) {
@@ -1909,6 +1952,29 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     if (d != 0.0) dirty = true;
     __syncthreads();
   };
+  // Order-preserving compaction of the non-zero entries of cs[0..m) (in place) and of their design
+  // columns (-> cks, aliasing `part`): the row combinations below skip members whose coefficient
+  // is (or stayed) zero -- exact zeros dropped from a sum leave it bit-identical.
+  int* cks = reinterpret_cast<int*>(part);
+  auto compact_nonzero = [&](double* cs, int m) -> int {
+    __syncthreads();
+    if (tid < 32) {
+      int base = 0;
+      for (int l0 = 0; l0 < m; l0 += 32) {
+        const int l = l0 + tid;
+        const double c = l < m ? cs[l] : 0.0;
+        const int k = l < m ? ia[l] : 0;
+        const unsigned b = __ballot_sync(0xffffffffu, c != 0.0);
+        const int pos = base + __popc(b & ((1u << tid) - 1u));
+        __syncwarp();
+        if (c != 0.0) { cs[pos] = c; cks[pos] = k; }
+        base += __popc(b);
+      }
+      if (tid == 0) ish[43] = base;
+    }
+    __syncthreads();
+    return ish[43];
+  };
   // bring the n-space residual up to date with the coefficients: wr -= w * (X~_A da + daz)
   auto materialise = [&](int m) {
     if (!dirty) return;
@@ -1922,10 +1988,11 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
     }
     bsum<1>(sh, red, phase);
     const double shift = (az - azmat) - sh[0];
+    const int mc = mlp ? compact_nonzero(amat, m) : m;  // members whose coefficient did not move add nothing
     for (int i = 2 * tid; i < ldx; i += 2 * T) {
       double s0 = shift, s1 = shift;
       if (mlp) {
-        const double2 sc = rows_comb(Xs + i, ldx, ia, amat, m, s0, s1);
+        const double2 sc = rows_comb(Xs + i, ldx, cks, amat, mc, s0, s1);
         s0 = sc.x;
         s1 = sc.y;
       } else
@@ -1944,7 +2011,7 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       r.y -= w.y * s1;
       *reinterpret_cast<double2*>(wrv + i) = r;
     }
-    ncols += m;
+    ncols += mc;
     __syncthreads();
     for (int l = tid; l < m; l += T) amat[l] = aact[l];
     azmat = az;
@@ -2382,12 +2449,13 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
       }
       bsum<1>(c0p, red, phase);
       const double c0 = az - c0p[0];
-      ncols += nin;
+      const int nz_in = mlp ? compact_nonzero(gq2, nin) : nin;
+      ncols += nz_in;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};  // sum w, sum t f, sum wr, held-out deviance
       for (int i = 2 * tid; i < ldx; i += 2 * T) {
         double f0 = c0, f1 = c0;
         if (mlp) {
-          const double2 fc2 = rows_comb(Xs + i, ldx, ia, gq2, nin, f0, f1);
+          const double2 fc2 = rows_comb(Xs + i, ldx, cks, gq2, nz_in, f0, f1);
           f0 = fc2.x;
           f1 = fc2.y;
         } else
@@ -2761,7 +2829,7 @@ int lasso_max_block(int NF, const DesignState& D, const LassoTuning& tune) {
   const double per_gene = NF * per_problem + (double)kNLam * (kNX * 8 + kMaxFolds * 8 + 32);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-    const double cap = ((double)free_b / 3.0 - (double)kHSlots * kNX * kNX * 8) / per_gene;
+    const double cap = ((double)free_b / 3.0 - (double)kHSlots * (kNX * kNX + kGramItems * 256) * 8) / per_gene;
     if (cap * NF < tot) tot = (int)(cap > 1.0 ? cap * NF : NF);
   }
   int b = tot / NF;
@@ -2794,7 +2862,8 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
                oCv = take((size_t)kNLam * kMaxFolds * B * 8), oL0 = take((size_t)P * 4),
                oL1 = take((size_t)P * 4), oCt = take(64), oCc = take(64),
                oIn = take((size_t)p_pad * P * 4), oHf = take((size_t)kHSlots * 4),
-               oHs = take((size_t)kHSlots * kNX * kNX * 8), oPh = take(512);
+               oHs = take((size_t)kHSlots * kNX * kNX * 8),
+               oHp = take((size_t)kHSlots * kGramItems * 256 * 8), oPh = take(512);
   cudaError_t e;
   if (off > ws.cap_bytes) {
     if (ws.base) {
@@ -2817,7 +2886,7 @@ cudaError_t lasso_run(const DesignState& D, LassoWs& ws, const LassoParams& prm,
   ws.ninp = (int*)(b + oNi); ws.nlpp = (int*)(b + oNp); ws.cap = (double*)(b + oCap); ws.cvdev = (double*)(b + oCv);
   ws.list0 = (int*)(b + oL0); ws.list1 = (int*)(b + oL1); ws.counters = (int*)(b + oCt);
   ws.colcount = (unsigned long long*)(b + oCc);
-  ws.INACT = (int*)(b + oIn); ws.hflags = (int*)(b + oHf); ws.Hs = (double*)(b + oHs);
+  ws.INACT = (int*)(b + oIn); ws.hflags = (int*)(b + oHf); ws.Hs = (double*)(b + oHs); ws.HP = (double*)(b + oHp);
   ws.phasecyc = (unsigned long long*)(b + oPh);
   for (auto& ev : ws.ev)
     if (!ev && (e = cudaEventCreate(&ev)) != cudaSuccess) return e;

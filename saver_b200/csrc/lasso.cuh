@@ -8,6 +8,7 @@ constexpr int kNX = 640;     // capacity of the ever-active list (glmnet pmax = 
 constexpr int kNLam = 128;   // capacity of a lambda sequence (glmnet nlambda = 100)
 constexpr int kMaxFolds = 16;
 constexpr int kCrumbSlots = 16384;
+constexpr int kGramItems = 256;  // (tile, row segment) items of one row-split Gram build
 
 // ST_HOLD: a fold fit that would get more than one lambda ahead of its gene's master fit waits (it
 // keeps its place in the problem list and is looked at again next round).
@@ -108,6 +109,7 @@ struct LassoWs {
   int *INACT;                // p_pad x P: inactive members of the strong set (gram kernel)
   int *hflags;               // Gram scratch slot flags
   double *Hs;                // Gram scratch: kHSlots x kNX x kNX
+  double *HP;                // partial Gram tiles of row-split builds: kHSlots x kGramItems x 256
   unsigned long long* phasecyc;  // [48] per-phase SM cycles of the gram kernel (bring-up / profiles)
   // accounting (host side, cumulative over the handle's life)
   double ms_round = 0, ms_gemm = 0, ms_setup = 0;
