@@ -2397,7 +2397,14 @@ lasso_round_gram_kernel(RoundArgs A, const int* __restrict__ list, int* __restri
         lap(4);
         crumb_m = m;
         crumb(6);
-        if (!(dbg & 8)) inactive_check(m, dlx, overflow);
+        // The inactive candidates are looked at once the active set has settled: while the
+        // index-order sweep still moves coefficients (dlx >= shr_in) the check -- a residual
+        // materialisation plus one pass over every inactive strong column -- would judge an
+        // intermediate residual; the phase cannot end without a check (dlx < shr_in is tested after
+        // it), so the strong-set KKT conditions hold at exit as before.  dbg bit 131072: check in
+        // every phase (fishnet1's order).
+        const bool settled = !(dlx >= shr_in) || m == 0 || (dbg & 131072);
+        if (!(dbg & 8) && settled) inactive_check(m, dlx, overflow);
         crumb_m = m;
         crumb(5);
         lap(5);

