@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 500 python scripts/probe_variants.py 256 "SAVER_LASSO_DBG=262272" "SAVER_LASSO_DBG=128" > gpurun_out/r2_lazy_ab.log 2>&1
+cat gpurun_out/r2_lazy_ab.log
+timeout 100 python scripts/probe_heavy.py "" >> gpurun_out/r2_lazy_ab.log 2>&1; tail -1 gpurun_out/r2_lazy_ab.log
