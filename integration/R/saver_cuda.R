@@ -7,7 +7,10 @@
 .saver.cuda <- new.env()
 saver.cuda.handle <- function() {
   if (is.null(.saver.cuda$h))
-    .saver.cuda$h <- .Call(C_saver_cuda_create, as.integer(getOption("saver.cuda.device", 0L)))
+    # options(saver.cuda.devices = 0:7): one R process, eight GPUs (blocks of calc.estimate are split
+    # over the devices inside the library); default: the single device saver.cuda.device
+    .saver.cuda$h <- .Call(C_saver_cuda_create,
+                           as.integer(getOption("saver.cuda.devices", getOption("saver.cuda.device", 0L))))
   .saver.cuda$h
 }
 

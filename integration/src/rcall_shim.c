@@ -51,10 +51,16 @@ static int *int_arg(SEXP x, R_xlen_t len, const char *what)
     return INTEGER(x);
 }
 
+/* device: one CUDA ordinal, or several -- then ONE R process drives all of them the way ncores =
+ * drives PSOCK workers (R/saver.R:120-138): saver_cuda_create_multi */
 SEXP C_saver_cuda_create(SEXP device)
 {
     saver_cuda_handle h = NULL;
-    int rc = saver_cuda_create(Rf_asInteger(device), &h);
+    int rc;
+    if (Rf_isInteger(device) && Rf_length(device) > 1)
+        rc = saver_cuda_create_multi(Rf_length(device), INTEGER(device), &h);
+    else
+        rc = saver_cuda_create(Rf_asInteger(device), &h);
     if (rc != SAVER_OK) Rf_error("no usable CUDA device (libsaver_cuda has no CPU fallback), code %d", rc);
     SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
