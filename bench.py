@@ -440,11 +440,7 @@ def run_cuda(args):
         "metric": METRIC, "value": value, "unit": "genes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tmax * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, w, B, p),
-                   "genes_per_step": int(B), "genes_per_step_per_gpu": int(np.ceil(B / world)),
-                   "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": "one gene block dealt round-robin over %d rank(s); design = one NCCL "
-                                  "broadcast; no data-path collective" % world},
+        "config": config_dict(args.workload, w, B, p, world),
         "clocks": clk,
         "e2e": {"value": B / e2e_max if e2e_max == e2e_max else None, "unit": "genes/s",
                 "h2d_bytes_per_step": int(sums[6]), "d2h_bytes_per_step": int(sums[7]),
@@ -478,6 +474,16 @@ def run_cuda(args):
     if comm is not None:
         comm.barrier()
         tdist.destroy_process_group()
+
+
+def config_dict(name, w, B, p, world):
+    """The `config` of the JSON line -- the same dict from both arms (the reference arm describes the
+    CUDA arm's workload; the L2 / parallelism entries say how the CUDA arm runs it)."""
+    return {"workload": workload_name(name, w, B, p),
+            "genes_per_step": int(B), "genes_per_step_per_gpu": int(np.ceil(B / world)),
+            "l2": "flushed between steps (256 MiB write)",
+            "parallelism": "one gene block dealt round-robin over %d rank(s); design = one NCCL "
+                           "broadcast; no data-path collective" % world}
 
 
 def workload_name(name, w, B, p):
@@ -553,7 +559,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot * 1e3 / max(len(times), 1),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, w, B, p)},
+        "config": config_dict(args.workload, w, B, p, world),
         "cpu_baseline": {"value": value, "unit": "genes/s", "cores": cores, "kind": "port",
                          "sample": sample + "; last step %.1f s" % last},
         "e2e": {"value": value, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
