@@ -9,8 +9,11 @@
 // and stats::cor in R/calc_maxcor.R:27.
 //
 // tcgen05 has no FP64 kind, so the exact contraction uses DMMA; operands are staged through
-// a 4-deep cp.async ring in shared memory, laid out [k-chunk][row][4] so that every m8n8k4
-// fragment load is one conflict-free, fully coalesced 256-byte LDS per warp.
+// a 4-deep cp.async ring in shared memory.  A stage keeps every operand row's 16 k-values
+// contiguous (eight 16-byte chunks, chunk index XORed with 4 on odd rows).  An m8n8k4 MMA may sum
+// any four k's as long as A and B agree, so lane (g, t) takes the k PAIR {2t, 2t+1} of its row
+// with ONE 16-byte LDS and feeds two MMAs (even k's, odd k's): 8 conflict-free LDS.128 per 32
+// DMMA, half the shared-memory instructions of one LDS.64 per fragment.
 //
 // Caller guarantees (the library allocates its panels that way): lda, ldb multiples of 16
 // with zero-filled padding rows up to Kp (multiple of 16); A has >= round_up(M,128) columns
@@ -44,26 +47,27 @@ __global__ void __launch_bounds__(GTHREADS, 2)
 gemm_tn_f64_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                    double* __restrict__ C, int ldc, int M, int N, int Kp) {
   extern __shared__ __align__(16) double sm[];
-  double* As = sm;                     // [STAGES][BK/4][BM][4]
-  double* Bs = sm + STAGES * A_STAGE;  // [STAGES][BK/4][BN][4]
+  double* As = sm;                     // [STAGES][BM][BK], chunks swizzled
+  double* Bs = sm + STAGES * A_STAGE;  // [STAGES][BN][BK]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps, 32 x 32 each
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const double* Ag = A + (size_t)m0 * lda;
   const double* Bg = B + (size_t)n0 * ldb;
 
+  // chunk q (k = 2q, 2q+1) of operand row r lives at r * 16 + 2 * (q ^ ((r & 1) << 2))
   auto load_stage = [&](int stage, int k0) {
     double* as = As + stage * A_STAGE;
     double* bs = Bs + stage * B_STAGE;
 #pragma unroll
     for (int i = 0; i < (BM * 8) / GTHREADS; ++i) {
       const int id = tid + GTHREADS * i, m = id >> 3, q = id & 7;
-      cp_async16(as + ((q >> 1) * BM + m) * 4 + (q & 1) * 2, Ag + (size_t)m * lda + k0 + 2 * q);
+      cp_async16(as + m * BK + 2 * (q ^ ((m & 1) << 2)), Ag + (size_t)m * lda + k0 + 2 * q);
     }
 #pragma unroll
     for (int i = 0; i < (BN * 8) / GTHREADS; ++i) {
       const int id = tid + GTHREADS * i, c = id >> 3, q = id & 7;
-      cp_async16(bs + ((q >> 1) * BN + c) * 4 + (q & 1) * 2, Bg + (size_t)c * ldb + k0 + 2 * q);
+      cp_async16(bs + c * BK + 2 * (q ^ ((c & 1) << 2)), Bg + (size_t)c * ldb + k0 + 2 * q);
     }
   };
 
@@ -73,6 +77,8 @@ gemm_tn_f64_kernel(const double* __restrict__ A, int lda, const double* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int swz = (g8 & 1) << 2;  // operand rows wm * 32 + i * 8 + g8 have the parity of g8
   const int KT = Kp / BK;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -85,19 +91,24 @@ gemm_tn_f64_kernel(const double* __restrict__ A, int lda, const double* __restri
     const int nxt = kt + STAGES - 1;
     if (nxt < KT) load_stage(nxt % STAGES, nxt * BK);
     cp_commit();
-    const double* as = As + (kt % STAGES) * A_STAGE;
-    const double* bs = Bs + (kt % STAGES) * B_STAGE;
+    const double* as = As + (kt % STAGES) * A_STAGE + (wm * 32 + g8) * BK;
+    const double* bs = Bs + (kt % STAGES) * B_STAGE + (wn * 32 + g8) * BK;
 #pragma unroll
-    for (int kc = 0; kc < BK / 4; ++kc) {
-      double a[4], b[4];
+    for (int kg = 0; kg < BK / 8; ++kg) {
+      const int off = 2 * ((kg * 4 + t4) ^ swz);
+      double2 a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = as[(kc * BM + wm * 32 + i * 8) * 4 + lane];
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 8 * BK + off);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = bs[(kc * BN + wn * 32 + j * 8) * 4 + lane];
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(bs + j * 8 * BK + off);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
     }
   }
   cp_wait<0>();
