@@ -26,9 +26,11 @@ Printed JSON (one line, rank 0):
             R's Brent; R and glmnet cannot be installed here) on a few genes of the block: its time is
             the CPU baseline, its results are the parity check of this very run.
 
-Other workloads: cfg2 (5,000 x 2,000, BASELINE.json configs[1]), null (saver(null.model = TRUE) on
-20,000 x 10,000: the variance-fit / posterior kernel alone), fast (do.fast = TRUE schedule on
-5,000 x 2,000), tiny.  --impl reference times the CPU restatement as the reference arm.
+Other workloads: cfg2 (5,000 x 2,000, BASELINE.json configs[1]), cfg4 (dgCMatrix 30,000 x 50,000,
+do.fast = TRUE, estimate + SE, a 2,048-gene block), cfg5 (sample.saver + cor.genes on 20,000 x 10,000
+est / se, genes sharded over the ranks), null (saver(null.model = TRUE) on 20,000 x 10,000: the
+variance-fit / posterior kernel alone), fast (do.fast = TRUE schedule on 5,000 x 2,000), tiny.
+--impl reference times the CPU restatement as the reference arm.
 """
 import argparse
 import json
