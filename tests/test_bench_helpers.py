@@ -40,3 +40,19 @@ def test_both_arms_name_the_same_config():
     assert a == b and a["genes_per_step"] == 512 and a["genes_per_step_per_gpu"] == 128
     assert "20000 genes x 10000 cells" in a["workload"] and "512 genes per step" in a["workload"]
     assert w["block"] == 512 and set(bench.WORKLOADS) >= {"cfg2", "cfg3", "cfg4", "cfg5", "null", "fast"}
+
+
+def test_sparse_generator_builds_a_canonical_dgcmatrix():
+    """bench_extra.sparse_nb_counts assembles the CSC slots chunk by chunk (cfg4's 30k x 50k matrix
+    never exists densely on the host): the result must be a canonical dgCMatrix -- column pointers
+    consistent, row indices sorted inside a column, no stored zeros -- with the model's sparsity."""
+    import torch
+
+    import bench_extra
+    x = bench_extra.sparse_nb_counts(300, 170, 7, torch.device("cpu"), torch, chunk=64)
+    assert x.shape == (300, 170) and x.format == "csc"
+    assert x.indptr[0] == 0 and x.indptr[-1] == x.nnz == x.data.size and (np.diff(x.indptr) >= 0).all()
+    assert x.has_canonical_format and (x.data > 0).all() and (x.data == np.rint(x.data)).all()
+    assert 0.1 < x.nnz / (300 * 170) < 0.7
+    y = bench_extra.sparse_nb_counts(300, 170, 7, torch.device("cpu"), torch, chunk=64)
+    assert (x != y).nnz == 0                      # seeded
